@@ -1,0 +1,298 @@
+"""Given-model ("f: audio -> y") encoders of the reference's audio_algebra/given_models.py, with the
+same class names, constructor arguments and encode() contract, computed by libaa_b200 on a B200.
+
+Mirrors /root/reference/audio_algebra/given_models.py:
+    GivenModelClass :58-145, SpectrogramAE :149-168, MagSpectrogramAE :171-189,
+    MagDPhaseSpectrogramAE :192-254, MelSpectrogramAE :257-283.
+Only the encode side is on the hot path; decode() raises.
+"""
+import ctypes as C
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+__all__ = ['GivenModelClass', 'SpectrogramAE', 'MagSpectrogramAE', 'MagDPhaseSpectrogramAE', 'MelSpectrogramAE']
+
+
+class GivenModelClass(nn.Module):
+    "Same optional 'shorthand' structure as the reference's GivenModelClass (given_models.py:58-82)"
+
+    def __init__(self, zero_pad=True, make_sizes_match=True,
+                 ckpt_info={'ckpt_path': '', 'ckpt_url': '', 'ckpt_hash': '', 'gdrive_path': ''}, **kwargs):
+        super().__init__()
+        self.make_sizes_match, self.orig_shape, self.zero_pad, self.ckpt_info = make_sizes_match, None, zero_pad, ckpt_info
+        self.name = self.__class__.__name__
+        self.ckpt_dir = os.path.expanduser('~/checkpoints')  # the reference creates it eagerly (:69-70); we do not
+
+    def setup(self, gdrive=True):
+        "Setup can include things such as downloading checkpoints (none needed for the STFT family)"
+        pass
+
+    def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
+        return None
+
+    def decode(self, reps: torch.Tensor, **kwargs) -> torch.Tensor:
+        raise NotImplementedError(f"{self.name}.decode is outside the accelerated hot path (encode side only)")
+
+    def forward(self, waveform: torch.Tensor):
+        "reference returns (reps, recons); recons needs the decoder, which is out of scope here"
+        reps = self.encode(waveform)
+        return (reps, self.decode(reps))
+
+    def match_sizes(self, recon) -> torch.Tensor:
+        "given_models.py:123-133, kept on the tensor's own device"
+        if self.make_sizes_match and (self.orig_shape is not None) and (recon.shape != self.orig_shape):
+            if recon.shape[-1] > self.orig_shape[-1]:
+                recon = recon[..., :self.orig_shape[-1]]
+            else:
+                recon2 = torch.zeros(self.orig_shape, device=recon.device, dtype=recon.dtype)
+                recon2[..., :recon.shape[-1]] = recon
+                recon = recon2
+            assert recon.shape == self.orig_shape, \
+                f"Did not succeed in making size match. recon.shape ({recon.shape}) != self.orig_shape ({self.orig_shape})"
+        return recon
+
+    def next_power_of_2(self, x: int) -> int:
+        return 1 if x == 0 else 2 ** (x - 1).bit_length()
+
+    def zero_pad_po2(self, x):
+        """given_models.py:139-145.  The CUDA front-ends never call this: the pad is folded into the
+        kernel's load.  Kept for API compatibility; stays on x's device."""
+        new_shape = list(x.shape)
+        new_shape[-1] = self.next_power_of_2(new_shape[-1])
+        new_x = torch.zeros(new_shape, device=x.device, dtype=x.dtype)
+        new_x[..., :x.shape[-1]] = x
+        return new_x
+
+
+# ---------------------------------------------------------------------------------------------------
+# mel filterbank (host side, once per module): torchaudio.functional.melscale_fbanks restated
+# ---------------------------------------------------------------------------------------------------
+
+def _hz_to_mel(freq, mel_scale):
+    if mel_scale == "htk":
+        return 2595.0 * math.log10(1.0 + (freq / 700.0))
+    f_min, f_sp = 0.0, 200.0 / 3
+    mels = (freq - f_min) / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = (min_log_hz - f_min) / f_sp
+    logstep = math.log(6.4) / 27.0
+    if freq >= min_log_hz:
+        mels = min_log_mel + math.log(freq / min_log_hz) / logstep
+    return mels
+
+
+def _mel_to_hz(mels, mel_scale):
+    if mel_scale == "htk":
+        return 700.0 * (10.0 ** (mels / 2595.0) - 1.0)
+    f_min, f_sp = 0.0, 200.0 / 3
+    freqs = f_min + f_sp * mels
+    min_log_hz = 1000.0
+    min_log_mel = (min_log_hz - f_min) / f_sp
+    logstep = math.log(6.4) / 27.0
+    log_t = mels >= min_log_mel
+    freqs[log_t] = min_log_hz * torch.exp(logstep * (mels[log_t] - min_log_mel))
+    return freqs
+
+
+def melscale_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate, norm=None, mel_scale="htk"):
+    "[n_freqs, n_mels] triangular filterbank, same formula and fp32 arithmetic as torchaudio"
+    if norm is not None and norm != "slaney":
+        raise ValueError('norm must be one of None or "slaney"')
+    if mel_scale not in ("htk", "slaney"):
+        raise ValueError('mel_scale should be one of "htk" or "slaney".')
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_pts = torch.linspace(_hz_to_mel(f_min, mel_scale), _hz_to_mel(f_max, mel_scale), n_mels + 2)
+    f_pts = _mel_to_hz(m_pts, mel_scale)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    zero = torch.zeros(1)
+    down_slopes = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up_slopes = slopes[:, 2:] / f_diff[1:]
+    fb = torch.max(zero, torch.min(down_slopes, up_slopes))
+    if norm == "slaney":
+        enorm = 2.0 / (f_pts[2:n_mels + 2] - f_pts[:n_mels])
+        fb = fb * enorm.unsqueeze(0)
+    return fb
+
+
+class _StftPlan:
+    "RAII holder of an AaStftPlan (one per module per device)"
+
+    def __init__(self, n_fft, hop, center, window, n_mels=0, sample_rate=48000.0, f_min=0.0, f_max=24000.0, fb=None):
+        self.handle = C.c_void_p()
+        win = None if window is None else window.detach().to("cpu", torch.float32).contiguous()
+        fbc = None if fb is None else fb.detach().to("cpu", torch.float32).contiguous()
+        check(lib.aa_stft_plan_create(C.byref(self.handle), int(n_fft), int(hop), int(bool(center)),
+                                      None if win is None else C.c_void_p(win.data_ptr()),
+                                      int(n_mels), float(sample_rate), float(f_min), float(f_max),
+                                      None if fbc is None else C.c_void_p(fbc.data_ptr())))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.aa_stft_plan_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def out_shape(self, n_in, zero_pad):
+        n_pad, n_frames = C.c_int64(), C.c_int64()
+        check(lib.aa_stft_out_shape(self.handle, int(n_in), int(bool(zero_pad)), C.byref(n_pad), C.byref(n_frames)))
+        return n_pad.value, n_frames.value
+
+
+class _StftFrontEnd(GivenModelClass):
+    """Shared plumbing of the three STFT encoders.  torchaudio kwargs understood: win_length,
+    window_fn, wkwargs (and for mel: n_mels, f_min, f_max, norm, mel_scale).  Options whose arithmetic
+    the kernels do not implement (pad != 0, normalized, pad_mode != 'reflect', onesided=False,
+    power not in the class's fixed value) raise instead of silently differing."""
+
+    def __init__(self, n_fft, hop_length, center, kwargs, mel=None):
+        super().__init__()
+        self.n_fft, self.hop_length, self.center = int(n_fft), int(hop_length), bool(center)
+        if self.n_fft < 64 or self.n_fft > 8192 or (self.n_fft & (self.n_fft - 1)) != 0:
+            raise _lib.AaError(f"n_fft={n_fft}: the CUDA STFT supports powers of two in [64, 8192]")
+        if self.hop_length < 1:
+            raise _lib.AaError(f"hop_length={hop_length} must be >= 1")
+        kw = dict(kwargs)
+        win_length = kw.pop("win_length", None) or self.n_fft
+        window_fn = kw.pop("window_fn", torch.hann_window)
+        wkwargs = kw.pop("wkwargs", None)
+        if kw.pop("pad", 0) != 0:
+            raise NotImplementedError("pad != 0 is not supported by the CUDA STFT front-end")
+        if kw.pop("normalized", False) not in (False, None):
+            raise NotImplementedError("normalized spectrograms are not supported by the CUDA STFT front-end")
+        if kw.pop("pad_mode", "reflect") != "reflect":
+            raise NotImplementedError("only pad_mode='reflect' is supported")
+        if kw.pop("onesided", True) is not True:
+            raise NotImplementedError("only onesided=True is supported")
+        window = window_fn(win_length) if wkwargs is None else window_fn(win_length, **wkwargs)
+        if win_length < self.n_fft:  # torch.stft centres a short window inside n_fft
+            left = (self.n_fft - win_length) // 2
+            w = torch.zeros(self.n_fft)
+            w[left:left + win_length] = window
+            window = w
+        elif win_length > self.n_fft:
+            raise ValueError("win_length must be <= n_fft")
+        self.register_buffer("window", window.float(), persistent=False)
+        self._mel = None
+        if mel is not None:
+            sample_rate = mel["sample_rate"]
+            self.n_mels = int(kw.pop("n_mels", 128))
+            self.f_min = float(kw.pop("f_min", 0.0))
+            f_max = kw.pop("f_max", None)
+            self.f_max = float(f_max) if f_max is not None else float(sample_rate // 2)
+            if kw.pop("power", 2.0) != 2.0:
+                raise NotImplementedError("MelSpectrogramAE computes the power (=2) mel spectrogram only")
+            norm, mel_scale = kw.pop("norm", None), kw.pop("mel_scale", "htk")
+            fb = melscale_fbanks(self.n_fft // 2 + 1, self.f_min, self.f_max, self.n_mels, sample_rate, norm, mel_scale)
+            self.register_buffer("fb", fb, persistent=False)
+            self._mel = dict(sample_rate=sample_rate)
+        if kw:
+            raise TypeError(f"unsupported keyword arguments for {self.__class__.__name__}: {sorted(kw)}")
+        self._plans = {}
+
+    def _plan(self, device_index):
+        if device_index not in self._plans:
+            with torch.cuda.device(device_index):
+                if self._mel is None:
+                    self._plans[device_index] = _StftPlan(self.n_fft, self.hop_length, self.center, self.window)
+                else:
+                    self._plans[device_index] = _StftPlan(self.n_fft, self.hop_length, self.center, self.window,
+                                                          self.n_mels, self._mel["sample_rate"], self.f_min, self.f_max,
+                                                          self.fb)
+        return self._plans[device_index]
+
+    def _run(self, waveform, mode):
+        """waveform [..., N] float32 -> [..., F|n_mels, T].  CUDA input: stream-ordered kernel on the
+        current stream.  CPU input: H2D, kernel, D2H (result returned on the CPU, like the reference
+        keeps the input's device) -- the mel variant pipelines the copies in chunks."""
+        self.orig_shape = waveform.shape
+        if waveform.dtype != torch.float32:
+            waveform = waveform.float()
+        on_cpu = not waveform.is_cuda
+        dev = _lib.ensure_device(None if on_cpu else waveform.device)
+        lead, n_in = waveform.shape[:-1], waveform.shape[-1]
+        rows = int(math.prod(lead)) if len(lead) else 1
+        plan = self._plan(dev)
+        n_pad, n_frames = plan.out_shape(n_in, self.zero_pad)
+        bins = self.n_mels if mode == "mel" else self.n_fft // 2 + 1
+        with torch.cuda.device(dev):
+            if on_cpu and mode == "mel":
+                x = waveform.contiguous()
+                out = torch.empty((*lead, bins, n_frames), dtype=torch.float32, pin_memory=True)
+                check(lib.aa_stft_mel_f32_host(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), 64))
+                return out
+            x = waveform.to(f"cuda:{dev}", non_blocking=True).contiguous()
+            if mode == "complex":
+                out = torch.empty((*lead, bins, n_frames), dtype=torch.complex64, device=x.device)
+                check(lib.aa_stft_complex_f32(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), stream_ptr()))
+            elif mode == "power":
+                out = torch.empty((*lead, bins, n_frames), dtype=torch.float32, device=x.device)
+                check(lib.aa_stft_power_f32(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), stream_ptr()))
+            else:
+                out = torch.empty((*lead, bins, n_frames), dtype=torch.float32, device=x.device)
+                check(lib.aa_stft_mel_f32(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), stream_ptr()))
+        return out.cpu() if on_cpu else out
+
+
+class SpectrogramAE(_StftFrontEnd):
+    "Raw (complex) spectrogram (given_models.py:149-168); encode -> complex64 [..., n_fft/2+1, frames]"
+
+    def __init__(self, n_fft=1024, hop_length=256, center=True, **kwargs):
+        super().__init__(n_fft, hop_length, center, kwargs)
+
+    def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
+        return self._run(waveform, "complex")
+
+
+class MagSpectrogramAE(_StftFrontEnd):
+    "Power spectrogram |X|^2 (given_models.py:171-189; torchaudio power=2)"
+
+    def __init__(self, n_fft=1024, hop_length=256, center=True, **kwargs):
+        super().__init__(n_fft, hop_length, center, kwargs)
+
+    def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
+        return self._run(waveform, "power")
+
+
+class MagDPhaseSpectrogramAE(_StftFrontEnd):
+    """Magnitude + phase-change spectrogram (given_models.py:192-254), use_cos=False branch.  Like the
+    reference, encode() is defined for unbatched [c, N] input and returns [2c, F, T]."""
+
+    def __init__(self, n_fft=1024, hop_length=256, center=True, init='true', use_cos=False, debug=False,
+                 cheat=False, **kwargs):
+        super().__init__(n_fft, hop_length, center, kwargs)
+        if use_cos:
+            raise NotImplementedError("use_cos=True (acos phase differences) is not on the accelerated path")
+        self.use_cos, self.cheat, self.debug, self.init = use_cos, cheat, debug, init
+        self.pi = 3.141592653589
+
+    def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
+        if waveform.dim() != 2:
+            raise ValueError("MagDPhaseSpectrogramAE.encode expects unbatched [channels, samples] input "
+                             "(the reference indexes dtheta[:,:,0] and concatenates on dim 0)")
+        on_cpu = not waveform.is_cuda
+        spec = self._run(waveform.cuda() if on_cpu else waveform, "complex")
+        c, f, t = spec.shape
+        out = torch.empty((2 * c, f, t), dtype=torch.float32, device=spec.device)
+        with torch.cuda.device(spec.device):
+            check(lib.aa_magdphase_f32(ptr(spec), c, f, t, ptr(out), stream_ptr()))
+        return out.cpu() if on_cpu else out
+
+
+class MelSpectrogramAE(_StftFrontEnd):
+    "Mel power spectrogram (given_models.py:257-283): torchaudio MelSpectrogram defaults (128 HTK bins)"
+
+    def __init__(self, sample_rate=48000, n_fft=1024, hop_length=256, center=True, **kwargs):
+        super().__init__(n_fft, hop_length, center, kwargs, mel=dict(sample_rate=sample_rate))
+        self.sample_rate = sample_rate
+
+    def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
+        return self._run(waveform, "mel")

@@ -1,0 +1,157 @@
+/*
+ * aa_b200.h -- C ABI of libaa_b200.so: the B200-native (sm_100a) implementation of the
+ * audio-algebra hot path (batched STFT/mel front-end, given-model conv encoder, AudioAlgebra
+ * projector, latent algebra and mixer/effects losses).
+ *
+ * The reference (drscotthawley/audio-algebra) is pure Python and has no FFI: its "plugin
+ * interface" for this path is the duck-typed Python protocol in audio_algebra/given_models.py
+ * (GivenModelClass.encode) and audio_algebra/aa_mixer.py (AudioAlgebra, do_mixing, losses).
+ * Every entry point below cites the reference lines whose arithmetic it replaces; the Python
+ * package `audio-algebra_b200/` binds them with ctypes and keeps the
+ * reference's class / function names.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all tensor pointers are DEVICE pointers unless the name ends
+ *    in `_host`; tensors are dense, row-major, the layouts given per function;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *    asynchronous and stream-ordered unless stated otherwise;
+ *  - return value: 0 = AA_OK, negative = AA_ERR_*; aa_last_error() returns a thread-local message;
+ *  - handles (AaStftPlan, AaEncoder) belong to the CUDA device that was current at creation and
+ *    are not internally locked; distinct handles / streams may be used concurrently.
+ */
+#ifndef AA_B200_H
+#define AA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AA_OK 0
+#define AA_ERR_INVALID_ARG (-1)  /* bad shape / null pointer / unsupported parameter combination */
+#define AA_ERR_CUDA (-2)         /* a CUDA runtime call failed; message holds cudaGetErrorString  */
+#define AA_ERR_UNSUPPORTED (-3)  /* valid request that this build has no kernel for               */
+#define AA_ERR_ARCH (-4)         /* device is not sm_100 (the library ships sm_100a code only)    */
+
+#define AA_DTYPE_F32 0
+#define AA_DTYPE_BF16 1
+
+int aa_version(void);
+const char* aa_last_error(void);
+/* 0 if the current device can run this library (compute capability 10.x), else AA_ERR_ARCH. */
+int aa_check_device(void);
+/* number of kernels this library has launched from the calling process (all threads) */
+int64_t aa_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * STFT / power / mel front-end.
+ * Replaces torchaudio.transforms.{Spectrogram,MelSpectrogram} as called from
+ * given_models.py:158 (SpectrogramAE, power=None), :180 (MagSpectrogramAE, power=2) and
+ * :267 (MelSpectrogramAE), and GivenModelClass.zero_pad_po2 (given_models.py:139-145), which is
+ * folded into the load (n_in -> n_pad = next power of two, never materialised).
+ * Semantics: torch.stft(center, pad_mode="reflect", win_length=n_fft, onesided, normalized=False);
+ * mel = fb^T |X|^2 with fb = melscale_fbanks(n_fft/2+1, f_min, f_max, n_mels, sample_rate,
+ * norm=None, mel_scale="htk").
+ * ------------------------------------------------------------------------------------------ */
+typedef struct AaStftPlan AaStftPlan;
+
+/* window_host: n_fft floats or NULL (periodic Hann).  fb_host: [n_fft/2+1][n_mels] floats or NULL
+ * (HTK triangular filterbank built internally).  n_mels = 0 for a plan without a mel stage.
+ * n_fft must be a power of two in [64, 8192]; hop >= 1. */
+int aa_stft_plan_create(AaStftPlan** plan, int n_fft, int hop, int center, const float* window_host,
+                        int n_mels, float sample_rate, float f_min, float f_max, const float* fb_host);
+int aa_stft_plan_destroy(AaStftPlan* plan);
+/* n_pad = zero_pad ? next_pow2(n_in) : n_in;  n_frames = center ? 1 + n_pad/hop : 1 + (n_pad-n_fft)/hop */
+int aa_stft_out_shape(const AaStftPlan* plan, int64_t n_in, int zero_pad, int64_t* n_pad, int64_t* n_frames);
+
+/* wav [rows][n_in] f32 -> out [rows][n_fft/2+1][n_frames] complex64 (interleaved re,im) */
+int aa_stft_complex_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                        float* out, void* stream);
+/* -> out [rows][n_fft/2+1][n_frames] f32 = |X|^2 */
+int aa_stft_power_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                      float* out, void* stream);
+/* -> out [rows][n_mels][n_frames] f32 */
+int aa_stft_mel_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                    float* out, void* stream);
+/* MagDPhaseSpectrogramAE.encode epilogue (given_models.py:214-231, use_cos=False): spec [c][F][T]
+ * complex64 -> out [2c][F][T] f32: magnitudes then phase differences along T (negative differences
+ * wrapped by +2*3.141592653589, frame 0 keeps the phase). */
+int aa_magdphase_f32(const float* spec, int64_t c, int64_t n_freq, int64_t n_frames, float* out, void* stream);
+/* End-to-end helper for the bulk encode loop (xae_dataset.ipynb cell 50): host wav -> host mel, chunked
+ * over rows, H2D / kernel / D2H overlapped on internal streams; synchronous on return.  Host buffers
+ * should be pinned for full PCIe bandwidth (pageable memory works, slower). */
+int aa_stft_mel_f32_host(const AaStftPlan* plan, const float* wav_host, int64_t rows, int64_t n_in, int zero_pad,
+                         float* out_host, int64_t rows_per_chunk);
+
+/* ------------------------------------------------------------------------------------------
+ * Latent algebra (aa_mixer.py:307 zsum; train_aa_effects.py:70-71 guesses; Destructo.ipynb
+ * cells 22, 48-49).  All tensors f32, n elements, contiguous.
+ * ------------------------------------------------------------------------------------------ */
+/* out[i] = sum_j coeffs_host[j] * zs[j][i], 1 <= n_terms <= 8; `zs_host` is a host array of device
+ * pointers.  out may alias any input. */
+int aa_latent_lincomb_f32(int n_terms, const float* const* zs_host, const float* coeffs_host, float* out,
+                          int64_t n, void* stream);
+#define AA_UNARY_SIGN_FOLD 0    /* max(z) * (sign(z) - z)        Destructo.ipynb cell 22 */
+#define AA_UNARY_ABSMAX_MINUS 1 /* max|z| - z                                            */
+#define AA_UNARY_TANH_DRIVE 2   /* max(z) * tanh(param * z)                              */
+#define AA_UNARY_FLIP_CHANNELS 3 /* z.flip(dims=[1]) on [B][C][T]; needs c,t               */
+#define AA_UNARY_FLIP_TIME 4    /* z.flip(dims=[2])                                      */
+/* workspace: >= 2 floats of device scratch (global max reductions). */
+int aa_latent_unary_f32(int op, const float* z, float* out, int64_t b, int64_t c, int64_t t, float param,
+                        float* workspace, void* stream);
+/* Destructo.ipynb cell 48-49: out[b] = emb[b] + mean_b'(wet[b'] - dry[b']); emb [B][C*T], wet/dry [Bw][C*T] */
+int aa_effect_transfer_f32(const float* emb, int64_t b, const float* wet, const float* dry, int64_t bw,
+                           int64_t ct, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses (aa_mixer.py:344-364; L2-hinge variant train_aa_effects.py:42-46).
+ * z is [B][D] f32 (D = C*T flattened features), the batch dimension is the statistics dimension.
+ * Each *_fwd writes ONE f32 scalar to `loss` (device) and is deterministic (no float atomics).
+ * ------------------------------------------------------------------------------------------ */
+/* mean((a-b)^2); workspace >= aa_reduce_workspace_floats() floats */
+int64_t aa_reduce_workspace_floats(void);
+int aa_mse_fwd_f32(const float* a, const float* b, int64_t n, float* loss, float* workspace, void* stream);
+/* grad_a[i] (+)= gscale * 2 (a-b)/n ; grad_b likewise with the opposite sign (either may be NULL) */
+int aa_mse_bwd_f32(const float* a, const float* b, int64_t n, const float* gloss, float gscale,
+                   float* grad_a, float* grad_b, int accumulate, void* stream);
+/* vicreg_var_loss: mean_d(relu(gamma - sqrt(var_unbiased_b(z[:,d]) + eps))) (hinge_l2: squared relu).
+ * Also emits per-feature mean and var (needed by bwd and by the cov loss): stats [2][D]. */
+int aa_vicreg_var_fwd_f32(const float* z, int64_t b, int64_t d, float gamma, float eps, int hinge_l2,
+                          float* loss, float* stats, float* workspace, void* stream);
+int aa_vicreg_var_bwd_f32(const float* z, const float* stats, int64_t b, int64_t d, float gamma, float eps,
+                          int hinge_l2, const float* gloss, float gscale, float* grad_z, int accumulate,
+                          void* stream);
+/* vicreg_cov_loss via the Gram identity: with X = z - mean_b(z) ([B][D]), G = X X^T ([B][B]),
+ *   sum_{i!=j} cov_ij^2 = (||G||_F^2 - sum_d (sum_b X_bd^2)^2) / (B-1)^2,  loss = that / D,
+ * instead of materialising the DxD covariance (aa_mixer.py:360-364).  gram: [B][B] f32 scratch that
+ * also feeds the backward; stats as produced by aa_vicreg_var_fwd_f32 (or NULL: computed internally
+ * into `stats_out`, [2][D]). */
+int aa_vicreg_cov_fwd_f32(const float* z, int64_t b, int64_t d, const float* stats, float* stats_out,
+                          float* gram, float* loss, float* workspace, void* stream);
+/* grad_z (+)= gscale * dL/dz,  dL/dX = 4/((B-1)^2 D) (G X - X diag(s)), s_d = sum_b X_bd^2, projected
+ * onto zero-mean columns. */
+int aa_vicreg_cov_bwd_f32(const float* z, const float* stats, const float* gram, int64_t b, int64_t d,
+                          const float* gloss, float gscale, float* grad_z, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PCA accumulation (calc_effects_pca.py:81-89): y [B][C][T] f32 -> cov_num [C][C] += C-by-C
+ * batch-centred scatter of the B*T points; count += B*T.  (eigh of the 64x64 result stays on host.)
+ * workspace: >= C*C*grid + 2*C floats, see aa_cov_workspace_floats.
+ * ------------------------------------------------------------------------------------------ */
+int64_t aa_cov_workspace_floats(int64_t c);
+int aa_cov_accumulate_f32(const float* y, int64_t b, int64_t c, int64_t t, float* cov_num, double* count,
+                          float* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser (train_aa_mixer_accel.py:481-482,533): torch.optim.Adam semantics on one flat f32
+ * buffer; step counts from 1.
+ * ------------------------------------------------------------------------------------------ */
+int aa_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AA_B200_H */

@@ -1,0 +1,167 @@
+"""GPU parity of the CUDA STFT / power / mel front-end (through the C ABI, via the reference-named
+Python classes) against (1) fixtures produced by the reference's own code, (2) the float64 oracle on
+seeded inputs, (3) size-independent properties at the full BASELINE config-2 size.
+Tolerance (BASELINE.json north_star): relative L2 <= 1e-4 on spectrograms, fp32."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # BASELINE.json: fp32 rel-L2 on spectrograms
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def aab():
+    import audio_algebra_b200 as aab
+    return aab
+
+
+def _oracle():
+    from oracle import aa_oracle as O
+    return O
+
+
+@pytest.mark.parametrize("tag,n_fft,hop", [("2048_512", 2048, 512), ("1024_256", 1024, 256)])
+def test_golden_small(aab, golden, tag, n_fft, hop):
+    g = golden("stft")
+    x = T(g["x_small"]).cuda()
+    c = aab.SpectrogramAE(n_fft=n_fft, hop_length=hop).encode(x)
+    assert c.dtype == torch.complex64 and tuple(c.shape) == g[f"complex_{tag}"].shape
+    assert rel_l2(c, g[f"complex_{tag}"]) < TOL
+    p = aab.MagSpectrogramAE(n_fft=n_fft, hop_length=hop).encode(x)
+    assert rel_l2(p, g[f"power_{tag}"]) < TOL
+    m = aab.MelSpectrogramAE(sample_rate=48000, n_fft=n_fft, hop_length=hop).encode(x)
+    assert tuple(m.shape) == g[f"mel_{tag}"].shape
+    assert rel_l2(m, g[f"mel_{tag}"]) < TOL
+
+
+def test_golden_non_pow2_length_defaults(aab, golden):
+    "given-models.ipynb cell 14 KAT: SpectrogramAE() on [2,55728] -> [2,513,257] complex64"
+    g = golden("stft")
+    x = T(g["x_np2"]).cuda()
+    s = aab.SpectrogramAE().encode(x)
+    assert tuple(s.shape) == (2, 513, 257) and s.dtype == torch.complex64
+    assert rel_l2(s[:, ::4, ::4], g["complex_np2_strided"]) < TOL
+    assert rel_l2(aab.MagSpectrogramAE().encode(x)[:, ::4, ::4], g["power_np2_strided"]) < TOL
+    assert rel_l2(aab.MelSpectrogramAE().encode(x), g["mel_np2"]) < TOL
+    # same signal through the fast n_fft=2048 path (edge tiles see the zero-padded tail)
+    O = _oracle()
+    for cls, fn in [(aab.MelSpectrogramAE, lambda v: O.mel_spectrogram(v, 48000, 2048, 512)),
+                    (aab.MagSpectrogramAE, lambda v: O.power_spectrogram(v, 2048, 512)),
+                    (aab.SpectrogramAE, lambda v: O.stft_complex(v, 2048, 512))]:
+        out = cls(n_fft=2048, hop_length=512).encode(x)
+        assert rel_l2(out, fn(x.cpu())) < TOL
+
+
+def test_golden_odd_rows_unaligned_length(aab, golden):
+    g = golden("stft")
+    x = T(g["x_odd"]).cuda()  # [3,1,5001]: odd row count, n_in % 4 != 0
+    assert rel_l2(aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512).encode(x), g["mel_odd_2048_512"]) < TOL
+    assert rel_l2(aab.MagSpectrogramAE().encode(x)[:, :, ::4, :], g["power_odd_1024_256"]) < TOL
+    O = _oracle()
+    assert rel_l2(aab.SpectrogramAE(n_fft=2048, hop_length=512).encode(x), O.stft_complex(x.cpu(), 2048, 512)) < TOL
+
+
+def test_golden_headline_chunk(aab, golden):
+    from oracle.make_golden import synth
+    g = golden("stft")
+    x = synth((1, 2, 131072), int(g["x_big_seed"][0])).cuda()
+    m = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512).encode(x)
+    assert tuple(m.shape) == (1, 2, 128, 257)
+    assert rel_l2(m, g["mel_big_2048_512"]) < TOL
+
+
+def test_magdphase(aab, golden):
+    g = golden("stft")
+    out = aab.MagDPhaseSpectrogramAE().encode(T(g["x_mdp"]).cuda()).cpu().double()
+    ref = T(g["magdphase"]).double()
+    c = ref.shape[0] // 2
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert rel_l2(out[:c], ref[:c]) < TOL
+    d = (out[c:] - ref[c:] + np.pi) % (2 * np.pi) - np.pi
+    strong = ref[:c] > 1e-2 * ref[:c].max()
+    assert d[strong].abs().max() < 2e-3
+
+
+@pytest.mark.parametrize("n_fft,hop,n", [(2048, 512, 16384), (2048, 256, 8192), (2048, 1024, 8192), (2048, 500, 9000),
+                                         (512, 128, 4096), (4096, 1024, 16384), (256, 64, 1000), (2048, 2048, 8192)])
+def test_oracle_sweep(aab, n_fft, hop, n):
+    "fast path (n_fft=2048, hop%4==0, hop<=1024) and generic path against the float64 oracle"
+    O = _oracle()
+    g = torch.Generator().manual_seed(n_fft + hop)
+    x = (torch.rand(3, 2, n, generator=g) * 2 - 1)
+    xc = x.cuda()
+    assert rel_l2(aab.SpectrogramAE(n_fft=n_fft, hop_length=hop).encode(xc), O.stft_complex(x, n_fft, hop)) < TOL
+    assert rel_l2(aab.MagSpectrogramAE(n_fft=n_fft, hop_length=hop).encode(xc), O.power_spectrogram(x, n_fft, hop)) < TOL
+    assert rel_l2(aab.MelSpectrogramAE(sample_rate=48000, n_fft=n_fft, hop_length=hop, n_mels=64).encode(xc),
+                  O.mel_spectrogram(x, 48000, n_fft, hop, n_mels=64)) < TOL
+
+
+def test_center_false_and_no_zero_pad(aab):
+    O = _oracle()
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 2, 6000, generator=g) - 0.5
+    m = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512, center=False)
+    m.zero_pad = False
+    ref = O.mel_spectrogram(x, 48000, 2048, 512, center=False, zero_pad=False)
+    out = m.encode(x.cuda())
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert rel_l2(out, ref) < TOL
+
+
+def test_cpu_input_goes_through_the_device_and_comes_back(aab, golden):
+    g = golden("stft")
+    x = T(g["x_small"])  # CPU tensor: H2D + kernel + D2H (the e2e path of bench.py)
+    m = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512).encode(x)
+    assert m.device.type == "cpu" and rel_l2(m, g["mel_2048_512"]) < TOL
+    s = aab.SpectrogramAE(n_fft=2048, hop_length=512).encode(x)
+    assert s.device.type == "cpu" and rel_l2(s, g["complex_2048_512"]) < TOL
+    big = torch.rand(150, 2, 8192) - 0.5   # several chunks of the pipelined host path, odd chunk tail
+    O = _oracle()
+    assert rel_l2(aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512).encode(big),
+                  O.mel_spectrogram(big, 48000, 2048, 512)) < TOL
+
+
+def test_empty_batch_and_errors(aab):
+    m = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512)
+    out = m.encode(torch.zeros(0, 2, 8192, device="cuda"))
+    assert tuple(out.shape) == (0, 2, 128, 17)
+    from audio_algebra_b200._lib import AaError
+    with pytest.raises(AaError):
+        m.encode(torch.zeros(1, 2, 512, device="cuda"))  # reflect pad needs > n_fft/2 samples
+    with pytest.raises(AaError):
+        aab.SpectrogramAE(n_fft=1000)  # not a power of two
+    with pytest.raises(NotImplementedError):
+        m.decode(torch.zeros(1))
+
+
+def test_full_size_properties(aab):
+    """BASELINE config 2 geometry: [256,2,131072] -> [256,2,128,257].  The oracle is checked on a
+    row subset; the whole tensor through size-independent properties: hop-shift equivariance of
+    interior frames, Parseval (sum of one-sided power = n_fft * sum (x w)^2) and scaling."""
+    O = _oracle()
+    B, n = 256, 131072
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = (torch.rand(B, 2, n, device="cuda", generator=g) - 0.5)
+    mel = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512)
+    m = mel.encode(x)
+    assert tuple(m.shape) == (B, 2, 128, 257) and torch.isfinite(m).all()
+    for b in (0, 97, 255):
+        assert rel_l2(m[b], O.mel_spectrogram(x[b].cpu(), 48000, 2048, 512)) < TOL
+    # shift by one hop: frame t of the shifted signal == frame t+1 of the original (interior frames)
+    xs = torch.roll(x, shifts=-512, dims=-1)
+    ms = mel.encode(xs)
+    assert rel_l2(ms[..., 2:250], m[..., 3:251]) < 1e-5
+    # mel is quadratic in the signal
+    assert rel_l2(mel.encode(2.0 * x), 4.0 * m) < 1e-6
+    # Parseval on the power spectrogram of a few rows (full rows would need 1 GB)
+    p = aab.MagSpectrogramAE(n_fft=2048, hop_length=512).encode(x[:8])
+    w = torch.hann_window(2048, periodic=True, device="cuda")
+    fr = torch.nn.functional.pad(x[:8].reshape(16, 1, n), (1024, 1024), mode="reflect").reshape(8, 2, -1).unfold(-1, 2048, 512)
+    energy = ((fr * w) ** 2).sum(-1) * 2048            # [8,2,257]
+    onesided = 2 * p.sum(dim=-2) - p[..., 0, :] - p[..., -1, :]
+    assert rel_l2(onesided, energy) < 1e-5
