@@ -5,24 +5,30 @@
 // and GivenModelClass.zero_pad_po2 (:139-145).
 //
 // Fast path (n_fft = 2048, hop % 4 == 0, hop <= 1024) -- `stft2048_kernel`:
-//   * one CTA = 4 warps = 4 consecutive frames of one ROW PAIR; the two rows ride in the two halves
-//     of packed fp32x2 registers, so the FFT arithmetic is FADD2/FFMA2 (one issue slot per 2 flops);
+//   * persistent CTAs (2 per SM) of 6 warps walk over tiles of 6 consecutive frames of one ROW PAIR;
+//     the two rows ride in the two halves of packed fp32x2 registers, so the FFT arithmetic is
+//     FADD2/FFMA2 (one issue slot per 2 flops); twiddle / window tables live in shared memory;
 //   * the tile's samples are brought into shared memory once per row by a TMA bulk copy
 //     (cp.async.bulk + mbarrier; reflect padding and the zero_pad_po2 tail are handled in index
 //     math on the few tiles at the chunk edges), so the 75 % frame overlap costs no extra HBM
-//     traffic inside a tile;
+//     traffic inside a tile; the next tile's copy is issued as soon as the current tile's samples
+//     are in registers and overlaps with the FFT;
 //   * a real 2048-point FFT is one 1024-point complex FFT: lane n2 holds z[32*n1+n2] (32 packed
 //     complex values), runs a 32-point in-register FFT, multiplies by W_1024^(n2*k1), transposes
 //     through a warp-private shared-memory buffer, runs the second 32-point FFT (lane k1 then holds
 //     Z[k1+32*k2]), and the even/odd split pairs lane k1 with lane 32-k1 through the same buffer;
-//   * epilogues: |X|^2 -> sparse (<= 2 taps per bin) mel projection from shared memory, or
-//     staged power / complex stores that write 16-byte runs along the frame axis.
+//   * epilogues: |X|^2 -> sparse (<= 2 taps per bin) mel projection from shared memory (quarter-warp =
+//     one filter x the tile's 6 frames, packed (rowA,rowB) FFMA2, conflict-free skewed P lines), or
+//     staged power / complex stores that write 24/48-byte runs along the frame axis.
 // Generic path (any power-of-two n_fft in [64, 8192]) -- `stft_generic_kernel`: one CTA per
 //   (row, frame), shared-memory radix-2 FFT; correct for every configuration, not tuned.
 #include "aa_common.cuh"
 #include "fft_gen.cuh"
+#include "stft_consts.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 namespace {
@@ -47,6 +53,10 @@ struct StftArgs {
   const float4* mel_w4;   // padded filter weights, pre-multiplied by 0.25 (P holds 4|X|^2)
   float* out;
   int wav_aligned16;
+  long long n_tiles;      // fast path: row pairs x tiles_per_pair
+  const int4* mel_steps;  // fast path: [kWarps][mel_steps_per_warp][2] step headers, then the step weights
+  int mel_steps_per_warp, mel_hdr_bytes, mel_w_bytes;
+  const float* lane_consts;  // fast path: float4[32] Hann phases + float2[32] W_2048^lane
 };
 
 __device__ __forceinline__ float fetch_sample(const float* __restrict__ p, long long i, long long n_in,
@@ -61,13 +71,18 @@ __device__ __forceinline__ float fetch_sample(const float* __restrict__ p, long 
 }
 
 // ------------------------------------------------------------------------------------------
-// Fast kernel, n_fft = 2048.
+// Fast kernel, n_fft = 2048: persistent CTAs of 6 warps; one warp = one frame of one row pair.
 // ------------------------------------------------------------------------------------------
-constexpr int kWarps = 4;                       // frames per CTA
+constexpr int kWarps = 6;                       // frames per tile
 constexpr int kThreads = kWarps * 32;
-constexpr int kXbBytes = 32 * 33 * 8;           // warp-private exchange buffer (float2 [32][33])
-constexpr int kPStride = 1028;                  // floats per (frame,row) line of the P staging area
-constexpr int kStageBytes = kWarps * kXbBytes;  // 33792 >= 8 * 1028 * 4 = 32896
+constexpr int kXbBytes = 32 * 33 * 8 + 16;      // warp-private exchange buffer (float2 [32][33]) + 16 B skew:
+                                                // consecutive frames' P lines start 4 banks apart
+constexpr int kPLine = kXbBytes / 8;            // float2 stride between the P lines of consecutive frames (1058)
+constexpr int kStageBytes = kWarps * kXbBytes;  // 50688
+constexpr int kTableBytes = 8192 + 512 + 256;   // tw1 [32][32] float2, per-lane Hann phases float4[32], W_2048^lane float2[32]
+constexpr int kCStride = 260;                   // complex-mode staging: [12 lines][260] float2
+
+static_assert(kPLine >= 1028, "a P line (1025 bins + pad) must fit in one exchange buffer");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -97,266 +112,371 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+struct TileGeom {
+  int rowA;         // first row of the pair
+  int s0;           // first sample (signal coordinates, may be negative / past the end)
+  int f0;
+  int lo, hi;       // [lo, hi): part of the tile's span that lies inside the row -> TMA (if `tma`)
+  bool hasB, tma;
+};
+
+// 32-bit on purpose (the host checks n_tiles, rows and n_pad fit).
+__device__ __forceinline__ TileGeom tile_geom(const StftArgs& a, int t, int span) {
+  TileGeom g;
+  const int pair = t / a.tiles_per_pair;
+  g.f0 = (t - pair * a.tiles_per_pair) * kWarps;
+  g.rowA = 2 * pair;
+  g.hasB = g.rowA + 1 < (int)a.rows;
+  g.s0 = g.f0 * a.hop - a.center_off;
+  g.lo = g.s0 < 0 ? -g.s0 : 0;
+  g.hi = min(span, (int)a.n_in - g.s0);
+  // bulk copies need 16-byte aligned source / destination / size: rows of n_in % 4 == 0 floats from an
+  // aligned base (hop % 4 == 0 and the centre offset 1024 keep s0 a multiple of 4)
+  g.tma = g.hasB && a.wav_aligned16 && ((int)a.n_in & 3) == 0 && g.hi - g.lo >= 4 && g.lo < span;
+  return g;
+}
+
+__device__ __forceinline__ void issue_tma(float* SA, float* SB, const float* src, int lo, int cnt, long long n_in,
+                                          uint64_t* mbar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(mbar, (uint32_t)cnt * 8u);
+  bulk_g2s(SA + lo, src, (uint32_t)cnt * 4u, mbar);
+  bulk_g2s(SB + lo, src + n_in, (uint32_t)cnt * 4u, mbar);
+}
+
+// Samples of the span outside [lo, hi) (chunk borders: reflect padding, zero_pad_po2 tail,
+// given_models.py:139-145) -- or the whole span when the tile cannot use TMA (odd last row, unaligned rows).
+__device__ __forceinline__ void load_tile_manual(const StftArgs& a, const TileGeom& g, int span, float* SA, float* SB,
+                                                 int tid) {
+  const float* __restrict__ pa = a.wav + (size_t)g.rowA * (size_t)a.n_in;
+  const int n_in = (int)a.n_in, n_pad = (int)a.n_pad;
+  const bool center = a.center_off != 0;
+  const int skip_lo = g.tma ? g.lo : 0, skip_hi = g.tma ? g.hi : 0;   // [skip_lo, skip_hi) is covered by TMA
+  const int n_out = span - (skip_hi - skip_lo);
+  for (int jj = tid; jj < n_out; jj += kThreads) {
+    const int j = jj < skip_lo ? jj : jj + (skip_hi - skip_lo);
+    int i = g.s0 + j;
+    if (center) {
+      if (i < 0) i = -i;
+      if (i >= n_pad) i = 2 * (n_pad - 1) - i;
+    }
+    const bool ok = i >= 0 && i < n_in;
+    SA[j] = ok ? __ldg(pa + i) : 0.f;
+    SB[j] = (ok && g.hasB) ? __ldg(pa + n_in + i) : 0.f;
+  }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3) stft2048_kernel(const StftArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = a.hop;
-  const int span = 3 * hop + 2048;              // samples covered by the 4 frames of this tile
+  const int span = (kWarps - 1) * hop + 2048;   // samples covered by the frames of one tile
   float* SA = reinterpret_cast<float*>(smem);                        // row A samples [span]
   float* SB = SA + span;                                             // row B samples [span]
   unsigned char* stage = smem + (size_t)span * 8;                    // kStageBytes
   float2* XB = reinterpret_cast<float2*>(stage + warp * kXbBytes);   // this warp's exchange buffer
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(stage + kStageBytes);
+  float2* s_tw1 = reinterpret_cast<float2*>(stage + kStageBytes);    // [32][32] W_1024^(k1 n2)
+  float4* s_lane = reinterpret_cast<float4*>(s_tw1 + 1024);          // [32] (cos,sin) of 2pi(2 lane + {0,1})/2048
+  float2* s_tw2l = reinterpret_cast<float2*>(s_lane + 32);           // [32] W_2048^lane
+  int4* s_melh = reinterpret_cast<int4*>(s_tw2l + 32);               // mel step headers [kWarps][steps][2]
+  float4* s_melw = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s_melh) + a.mel_hdr_bytes);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_melw) + a.mel_w_bytes);
+  constexpr bool kPrefetch = (MODE != MODE_COMPLEX);  // complex mode reuses the sample area as staging
 
-  const long long pair = blockIdx.x / a.tiles_per_pair;
-  const int tile = blockIdx.x % a.tiles_per_pair;
-  const int f0 = tile * kWarps;
-  const long long rowA = 2 * pair, rowB = rowA + 1;
-  const bool hasB = rowB < a.rows;
-  const float* __restrict__ pa = a.wav + rowA * a.n_in;
-  const float* __restrict__ pb = hasB ? a.wav + rowB * a.n_in : nullptr;
-  const long long s0 = (long long)f0 * hop - a.center_off;
-  const bool center = a.center_off != 0;
+  for (int i = tid; i < 1024; i += kThreads) s_tw1[i] = __ldg(a.tw1 + i);
+  if (tid < 48) reinterpret_cast<float4*>(s_lane)[tid] = __ldg(reinterpret_cast<const float4*>(a.lane_consts) + tid);
+  for (int i = tid; i < (a.mel_hdr_bytes + a.mel_w_bytes) / 16; i += kThreads)
+    s_melh[i] = __ldg(a.mel_steps + i);   // headers and weights are one contiguous device block
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
-  // ---- stage the tile's samples ---------------------------------------------------------------
-  if (s0 >= 0 && s0 + span <= a.n_in && hasB && a.wav_aligned16 && (a.n_in & 3) == 0) {
-    if (tid == 0) {
-      mbar_init(mbar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbar_expect_tx(mbar, (uint32_t)span * 8u);
-      bulk_g2s(SA, pa + s0, (uint32_t)span * 4u, mbar);
-      bulk_g2s(SB, pb + s0, (uint32_t)span * 4u, mbar);
-    }
-    __syncthreads();          // barrier init visible to every waiter
-    mbar_wait(mbar, 0);
-  } else {                    // chunk edges / odd row count / unaligned rows: reflect + zero tail
-    for (int j = tid; j < span; j += kThreads) {
-      SA[j] = fetch_sample(pa, s0 + j, a.n_in, a.n_pad, center);
-      SB[j] = fetch_sample(pb, s0 + j, a.n_in, a.n_pad, center);
-    }
-    __syncthreads();
+  uint32_t phase = 0;
+  const int n_tiles = (int)a.n_tiles;
+  if ((int)blockIdx.x >= n_tiles) return;
+  if (tid == 0) {
+    const TileGeom g0 = tile_geom(a, blockIdx.x, span);
+    if (g0.tma)
+      issue_tma(SA, SB, a.wav + (size_t)g0.rowA * (size_t)a.n_in + (g0.s0 + g0.lo), g0.lo, g0.hi - g0.lo, a.n_in, mbar);
   }
 
-  const int frame = f0 + warp;
-  const bool fvalid = frame < a.n_frames;
-
-  float2 re[32], im[32];
-  if (fvalid) {
-    // ---- load + window: z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1], n = 32*n1 + lane ------------
-    const float2* FA = reinterpret_cast<const float2*>(SA + warp * hop);
-    const float2* FB = reinterpret_cast<const float2*>(SB + warp * hop);
-#pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1) {
-      const int n = 32 * n1 + lane;
-      const float2 xa = FA[n], xb = FB[n];
-      const float2 w = __ldg(a.window2 + n);
-      re[bitrev5(n1)] = make_float2(xa.x * w.x, xb.x * w.x);
-      im[bitrev5(n1)] = make_float2(xa.y * w.y, xb.y * w.y);
-    }
-    fft32_dit(re, im);  // slot k1: sum_n1 z[32 n1 + lane] W_32^(n1 k1)
-    // ---- twiddle W_1024^(lane*k1) ------------------------------------------------------------
-#pragma unroll
-    for (int k1 = 1; k1 < 32; ++k1) {
-      const float2 t = __ldg(a.tw1 + k1 * 32 + lane);
-      const float2 r = re[k1], i = im[k1];
-      re[k1] = pfma(i, -t.y, pmuls(r, t.x));
-      im[k1] = pfma(i, t.x, pmuls(r, t.y));
-    }
-    // ---- transpose through the warp-private buffer (re half, then im half) ----------------------
-#pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) XB[k1 * 33 + lane] = re[k1];
-    __syncwarp();
-#pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) re[bitrev5(n2)] = XB[lane * 33 + n2];
-    __syncwarp();
-#pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) XB[k1 * 33 + lane] = im[k1];
-    __syncwarp();
-#pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) im[bitrev5(n2)] = XB[lane * 33 + n2];
-    __syncwarp();
-    fft32_dit(re, im);  // slot k2 of lane k1: Z[k1 + 32 k2]
-    // ---- publish the upper half (k2 >= 16) for the partner lane ------------------------------------
-    float4* XB4 = reinterpret_cast<float4*>(XB);
-#pragma unroll
-    for (int k2 = 16; k2 < 32; ++k2)
-      XB4[(k2 - 16) * 32 + lane] = make_float4(re[k2].x, re[k2].y, im[k2].x, im[k2].y);
-    __syncwarp();
-  }
-
-  // Even/odd split for the pair (k, 1024-k), k = lane + 32 i (i < 16): own Z[k] in slot i, partner's
-  // Z[1024-k] in lane (32-lane)&31 slot 31-i (lane 0: slot 32-i).  With E2 = a + conj(b),
-  // O2 = (a - conj(b))/i, T = W_2048^k O2:  2 X[k] = E2 + T,  2 X[1024-k] = conj(E2 - T).
-  const int plane = (32 - lane) & 31;
-  const int pshift = (lane == 0) ? 16 : 15;  // partner slot - 16 = pshift - i
-  const float4* XB4r = reinterpret_cast<const float4*>(XB);
-
-  if constexpr (MODE == MODE_COMPLEX) {
-    // Four k-quarters, each staged as [8 (frame,row)][260] complex in the (now dead) sample area and
-    // stored with lanes = (8 bins) x (4 frames) so that every (row, bin) gets one 32-byte run.
-    float2* CS = reinterpret_cast<float2*>(smem);
-    constexpr int kCStride = 260;
-    const long long rowbase = rowA;
 #pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      __syncthreads();  // sample area (q = 0) / previous quarter's staging is free
-      if (fvalid) {
-        const bool upper = q >= 2;               // quarters 2,3 emit X[1024-k]
-        const int ibase = (q == 0 || q == 3) ? 0 : 8;
-        const int kq0 = q * 256;                 // staged bins: [kq0, kq0+256) (q=3: +1024)
-        float2* c0 = CS + (warp * 2 + 0) * kCStride;
-        float2* c1 = CS + (warp * 2 + 1) * kCStride;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    // ---- this tile's samples: the in-row part was prefetched by TMA; the reflected / zero-padded rest of
+    // an edge tile (or a whole tile that cannot use TMA) is filled in here --------------------------------
+    const TileGeom g = tile_geom(a, t, span);
+    if (!g.tma || g.lo > 0 || g.hi < span) {
+      load_tile_manual(a, g, span, SA, SB, tid);
+      __syncthreads();
+    }
+    if (g.tma) {
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+    }
+    if (kPrefetch && tid == 0) {   // decide the next prefetch now, while registers are free; park it in smem
+      const int tn = t + (int)gridDim.x;
+      unsigned long long src = 0ull, rng = 0ull;
+      if (tn < n_tiles) {
+        const TileGeom gn = tile_geom(a, tn, span);
+        if (gn.tma) {
+          src = reinterpret_cast<unsigned long long>(a.wav + (size_t)gn.rowA * (size_t)a.n_in + (gn.s0 + gn.lo));
+          rng = (unsigned long long)(unsigned)gn.lo | ((unsigned long long)(unsigned)(gn.hi - gn.lo) << 32);
+        }
+      }
+      mbar[1] = src;
+      mbar[2] = rng;
+    }
+    const int f0 = g.f0;
+    const long long rowA = g.rowA;   // 64-bit for output addressing
+    const int frame = f0 + warp;
+    const bool fvalid = frame < a.n_frames;
+
+    float2 re[32], im[32];
+    if (fvalid) {
+      // ---- load + window: z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1], n = 32*n1 + lane ------------
+      // periodic Hann on the fly: w[j] = 0.5 - 0.5 cos(2 pi n1/32 + phi), phi = 2 pi (2 lane + {0,1})/2048
+      const float2* FA = reinterpret_cast<const float2*>(SA + warp * hop);
+      const float2* FB = reinterpret_cast<const float2*>(SB + warp * hop);
+      const float4 ph = s_lane[lane];   // (cos phi0, sin phi0, cos phi1, sin phi1)
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-          // register arrays need compile-time indices: select by (uniform) ibase
-          const float2 ar = (ibase == 0) ? re[ii] : re[ii + 8];
-          const float2 ai = (ibase == 0) ? im[ii] : im[ii + 8];
-          const int i = ibase + ii;
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const int n = 32 * n1 + lane;
+        const float2 xa = FA[n], xb = FB[n];
+        const float w0 = fmaf(0.5f * aa_consts::kSin32[n1], ph.y, fmaf(-0.5f * aa_consts::kCos32[n1], ph.x, 0.5f));
+        const float w1 = fmaf(0.5f * aa_consts::kSin32[n1], ph.w, fmaf(-0.5f * aa_consts::kCos32[n1], ph.z, 0.5f));
+        re[bitrev5(n1)] = make_float2(xa.x * w0, xb.x * w0);
+        im[bitrev5(n1)] = make_float2(xa.y * w1, xb.y * w1);
+      }
+    }
+    __syncthreads();  // samples consumed by every warp; previous tile's epilogue has left the staging area
+    if (kPrefetch && tid == 0) {   // next interior tile: TMA overlaps with the FFT below
+      const float* src = reinterpret_cast<const float*>(mbar[1]);
+      const unsigned long long rng = mbar[2];
+      if (src != nullptr) issue_tma(SA, SB, src, (int)(rng & 0xffffffffu), (int)(rng >> 32), a.n_in, mbar);
+    }
+
+    if (fvalid) {
+      fft32_dit(re, im);  // slot k1: sum_n1 z[32 n1 + lane] W_32^(n1 k1)
+      // ---- twiddle W_1024^(lane*k1) ------------------------------------------------------------
+#pragma unroll
+      for (int k1 = 1; k1 < 32; ++k1) {
+        const float2 tw = s_tw1[k1 * 32 + lane];
+        const float2 r = re[k1], i = im[k1];
+        re[k1] = pfma(i, -tw.y, pmuls(r, tw.x));
+        im[k1] = pfma(i, tw.x, pmuls(r, tw.y));
+      }
+      // ---- transpose through the warp-private buffer (re half, then im half) ----------------------
+#pragma unroll
+      for (int k1 = 0; k1 < 32; ++k1) XB[k1 * 33 + lane] = re[k1];
+      __syncwarp();
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) re[bitrev5(n2)] = XB[lane * 33 + n2];
+      __syncwarp();
+#pragma unroll
+      for (int k1 = 0; k1 < 32; ++k1) XB[k1 * 33 + lane] = im[k1];
+      __syncwarp();
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) im[bitrev5(n2)] = XB[lane * 33 + n2];
+      __syncwarp();
+      fft32_dit(re, im);  // slot k2 of lane k1: Z[k1 + 32 k2]
+      // ---- publish the upper half (k2 >= 16) for the partner lane ------------------------------------
+      float4* XB4 = reinterpret_cast<float4*>(XB);
+#pragma unroll
+      for (int k2 = 16; k2 < 32; ++k2)
+        XB4[(k2 - 16) * 32 + lane] = make_float4(re[k2].x, re[k2].y, im[k2].x, im[k2].y);
+      __syncwarp();
+    }
+
+    // Even/odd split for the pair (k, 1024-k), k = lane + 32 i (i < 16): own Z[k] in slot i, partner's
+    // Z[1024-k] in lane (32-lane)&31 slot 31-i (lane 0: slot 32-i).  With E2 = a + conj(b),
+    // O2 = (a - conj(b))/i, T = W_2048^k O2:  2 X[k] = E2 + T,  2 X[1024-k] = conj(E2 - T).
+    const int plane = (32 - lane) & 31;
+    const int pshift = (lane == 0) ? 16 : 15;  // partner slot - 16 = pshift - i
+    const float4* XB4r = reinterpret_cast<const float4*>(XB);
+
+    if constexpr (MODE == MODE_COMPLEX) {
+      // Four k-quarters, each staged as [12 (frame,row)][260] complex in the (now dead) sample area and
+      // stored with lanes = (32 bins) x (6 frames) so that every (row, bin) gets one 48-byte run.
+      float2* CS = reinterpret_cast<float2*>(smem);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        if (q > 0) __syncthreads();  // previous quarter's staging has been stored
+        if (fvalid) {
+          const bool upper = q >= 2;               // quarters 2,3 emit X[1024-k]
+          const int ibase = (q == 0 || q == 3) ? 0 : 8;
+          const int kq0 = q * 256;
+          float2* c0 = CS + (warp * 2 + 0) * kCStride;
+          float2* c1 = CS + (warp * 2 + 1) * kCStride;
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const float2 ar = (ibase == 0) ? re[ii] : re[ii + 8];
+            const float2 ai = (ibase == 0) ? im[ii] : im[ii + 8];
+            const int i = ibase + ii;
+            int ps = pshift - i;
+            ps = ps > 15 ? 15 : ps;
+            const float4 b = XB4r[ps * 32 + plane];
+            const float2 br = make_float2(b.x, b.y), bi = make_float2(b.z, b.w);
+            const int k = lane + 32 * i;
+            const float2 cl = s_tw2l[lane];
+            const float c64 = (ibase == 0) ? aa_consts::kCos64[ii] : aa_consts::kCos64[ii + 8];
+            const float s64 = (ibase == 0) ? aa_consts::kSin64[ii] : aa_consts::kSin64[ii + 8];
+            const float2 tw = make_float2(fmaf(cl.y, s64, cl.x * c64), fmaf(cl.y, c64, -cl.x * s64));
+            const float2 e_r = padd(ar, br), e_i = psub(ai, bi);
+            const float2 o_r = padd(ai, bi), o_i = psub(br, ar);
+            float2 xr, xi;
+            if (!upper) {  // X[k] = (E2 + T)/2
+              xr = pfma(o_i, -tw.y, pfma(o_r, tw.x, e_r));
+              xi = pfma(o_r, tw.y, pfma(o_i, tw.x, e_i));
+            } else {       // X[1024-k] = conj(E2 - T)/2
+              xr = pfma(o_i, tw.y, pfma(o_r, -tw.x, e_r));
+              xi = psub(pfma(o_r, tw.y, pmuls(o_i, tw.x)), e_i);
+            }
+            xr = pmuls(xr, 0.5f);
+            xi = pmuls(xi, 0.5f);
+            const int kk = (upper ? 1024 - k : k) - kq0;   // 0..256
+            if (!(lane == 0 && i == 0)) {
+              c0[kk] = make_float2(xr.x, xi.x);
+              c1[kk] = make_float2(xr.y, xi.y);
+            }
+          }
+          if (lane == 0) {
+            if (q == 0) {            // DC
+              c0[0] = make_float2(re[0].x + im[0].x, 0.f);
+              c1[0] = make_float2(re[0].y + im[0].y, 0.f);
+            } else if (q == 3) {     // Nyquist (bin 1024 -> index 256)
+              c0[256] = make_float2(re[0].x - im[0].x, 0.f);
+              c1[256] = make_float2(re[0].y - im[0].y, 0.f);
+            } else if (q == 2) {     // bin 512 = conj(Z[512]) (lane 0, slot 16)
+              c0[0] = make_float2(re[16].x, -im[16].x);
+              c1[0] = make_float2(re[16].y, -im[16].y);
+            }
+          }
+        }
+        __syncthreads();
+        // q=0: bins [0,256)  q=1: [256,512)  q=2: [512,768] (idx 0..256)  q=3: (768,1024] (idx 1..256)
+        const int lo = (q == 3) ? 1 : 0;
+        const int hi = (q >= 2) ? 257 : 256;
+        const int fsub = tid % kWarps, ksub = tid / kWarps;   // 32 bins x 6 frames per pass
+        const int fr = f0 + fsub;
+        if (fr < a.n_frames) {
+          for (int r = 0; r < 2; ++r) {
+            if (rowA + r >= a.rows) break;
+            float2* obase = reinterpret_cast<float2*>(a.out) + (rowA + r) * (long long)a.n_freq * a.n_frames + fr;
+            const float2* cl = CS + (fsub * 2 + r) * kCStride;
+            for (int kb = lo + ksub; kb < hi; kb += 32) obase[(long long)(q * 256 + kb) * a.n_frames] = cl[kb];
+          }
+        }
+      }
+      __syncthreads();  // staging (= sample area) free again
+      if (t + (int)gridDim.x < n_tiles && tid == 0) {
+        const TileGeom gn = tile_geom(a, t + gridDim.x, span);
+        if (gn.tma)
+          issue_tma(SA, SB, a.wav + (size_t)gn.rowA * (size_t)a.n_in + (gn.s0 + gn.lo), gn.lo, gn.hi - gn.lo, a.n_in, mbar);
+      }
+    } else {
+      // ---- power of every bin.  The P line of this frame (float2 = (rowA,rowB) per bin, 4|X|^2) is
+      // written into this warp's OWN exchange buffer: 4|X[1024-k]|^2 right away (those addresses are
+      // already consumed), 4|X[k]|^2 after the last partner read. ---------------------------------
+      float2* pl = reinterpret_cast<float2*>(stage + warp * kXbBytes);
+      if (fvalid) {
+        float2 pk[16];
+        const float2 z0r = re[0], z0i = im[0], z16r = re[16], z16i = im[16];
+        const float2 cl = s_tw2l[lane];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
           int ps = pshift - i;
           ps = ps > 15 ? 15 : ps;
           const float4 b = XB4r[ps * 32 + plane];
+          __syncwarp();   // all lanes have read slot row `ps` before anyone overwrites it below
           const float2 br = make_float2(b.x, b.y), bi = make_float2(b.z, b.w);
-          const int k = lane + 32 * i;
-          const float2 t = __ldg(a.tw2 + k);
+          const float2 ar = re[i], ai = im[i];
+          // W_2048^(lane + 32 i) = W_2048^lane * W_64^i
+          const float2 tw = make_float2(fmaf(cl.y, aa_consts::kSin64[i], cl.x * aa_consts::kCos64[i]),
+                                        fmaf(cl.y, aa_consts::kCos64[i], -cl.x * aa_consts::kSin64[i]));
           const float2 e_r = padd(ar, br), e_i = psub(ai, bi);
           const float2 o_r = padd(ai, bi), o_i = psub(br, ar);
-          float2 xr, xi;
-          if (!upper) {  // X[k] = (E2 + T)/2
-            xr = pfma(o_i, -t.y, pfma(o_r, t.x, e_r));
-            xi = pfma(o_r, t.y, pfma(o_i, t.x, e_i));
-          } else {       // X[1024-k] = conj(E2 - T)/2
-            xr = pfma(o_i, t.y, pfma(o_r, -t.x, e_r));
-            xi = psub(pfma(o_r, t.y, pmuls(o_i, t.x)), e_i);
-          }
-          xr = pmuls(xr, 0.5f);
-          xi = pmuls(xi, 0.5f);
-          const int kk = (upper ? 1024 - k : k) - kq0;   // 0..256
-          if (!(lane == 0 && i == 0)) {
-            c0[kk] = make_float2(xr.x, xi.x);
-            c1[kk] = make_float2(xr.y, xi.y);
-          }
+          const float2 xr = pfma(o_i, -tw.y, pfma(o_r, tw.x, e_r));   // Re(E2 + T)
+          const float2 xi = pfma(o_r, tw.y, pfma(o_i, tw.x, e_i));    // Im(E2 + T)
+          const float2 yr = pfma(o_i, tw.y, pfma(o_r, -tw.x, e_r));   // Re(E2 - T)
+          const float2 yi = pfma(o_r, -tw.y, pfma(o_i, -tw.x, e_i));  // Im(E2 - T)
+          pk[i] = pfma2(xi, xi, pmul(xr, xr));
+          const float2 pq = pfma2(yi, yi, pmul(yr, yr));
+          // bins 1024-k >= 513: byte offsets >= 4104 - 256 i, above every partner row still to be read
+          if (!(lane == 0 && i == 0)) pl[1024 - (lane + 32 * i)] = pq;
+          // partner rows still unread after this iteration cover bytes [0, 512 (16-i)) (lane 0 runs one
+          // row behind): pk[j] (bytes [256 j, 256 j + 256)) may go out once j >= 32 - 2 i
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j <= i && j >= 32 - 2 * i && (j == i || j < 34 - 2 * i)) pl[lane + 32 * j] = pk[j];
         }
-        if (lane == 0) {
-          if (q == 0) {            // DC
-            c0[0] = make_float2(re[0].x + im[0].x, 0.f);
-            c1[0] = make_float2(re[0].y + im[0].y, 0.f);
-          } else if (q == 3) {     // Nyquist (bin 1024 -> index 256)
-            c0[256] = make_float2(re[0].x - im[0].x, 0.f);
-            c1[256] = make_float2(re[0].y - im[0].y, 0.f);
-          } else if (q == 2) {     // bin 512 = conj(Z[512]) (lane 0, slot 16)
-            c0[0] = make_float2(re[16].x, -im[16].x);
-            c1[0] = make_float2(re[16].y, -im[16].y);
-          }
+        __syncwarp();
+        pl[lane] = pk[0];
+        pl[lane + 32] = pk[1];
+        __syncwarp();
+        if (lane == 0) {  // DC, Nyquist, bin 512, zero tail of the last float4 group
+          const float2 dc = padd(z0r, z0i), ny = psub(z0r, z0i);
+          pl[0] = pmuls(pmul(dc, dc), 4.f);
+          pl[1024] = pmuls(pmul(ny, ny), 4.f);
+          pl[512] = pmuls(pfma2(z16i, z16i, pmul(z16r, z16r)), 4.f);
+          pl[1025] = pl[1026] = pl[1027] = make_float2(0.f, 0.f);
         }
       }
       __syncthreads();
-      // bins staged this quarter: q=0: [0,256) q=1: [256,512) q=2: [512,768]->idx 0..256 minus... see below
-      // q=2 stages bins 1024-k for k in [256,512) => (512,768] plus bin 512 => idx 0..256
-      // q=3 stages bins 1024-k for k in [0,256)   => (768,1024] plus 1024   => idx 1..256
-      const int lo = (q == 3) ? 1 : 0;
-      const int hi = (q >= 2) ? 257 : 256;
-      const int fsub = tid & 3, ksub = (tid >> 2) & 7, grp = tid >> 5;  // 4 groups of (8 bins x 4 frames)
-      const int fr = f0 + fsub;
-      for (int r = 0; r < 2; ++r) {
-        if (rowbase + r >= a.rows) break;
-        float2* obase = reinterpret_cast<float2*>(a.out) + (rowbase + r) * (long long)a.n_freq * a.n_frames;
-        for (int kb = lo + grp * 8 + ksub; kb < hi; kb += 32) {
-          if (fr < a.n_frames) {
-            const float2 v = CS[(fsub * 2 + r) * kCStride + kb];
-            obase[(long long)(q * 256 + kb) * a.n_frames + fr] = v;
+      const float2* P = reinterpret_cast<const float2*>(stage);   // frame f at P + f * kPLine
+
+      if constexpr (MODE == MODE_MEL) {
+        // Each warp walks its own list of steps; a step = 4 adjacent mel filters (one per quarter-warp),
+        // lanes of a quarter-warp = the 6 frames of the tile (2 lanes idle).  A quarter-warp reads 16 B from
+        // 6 different P lines (skewed by 16 B) -> conflict-free; step headers and weights (one float4 per 4
+        // bins, zero-padded to the longest filter of the step) live in shared memory; accumulators are
+        // packed (rowA,rowB) FFMA2.
+        const int q = lane >> 3, fl = lane & 7;
+        const bool factive = fl < kWarps;
+        const float4* pf = reinterpret_cast<const float4*>(P + (factive ? fl : 0) * kPLine);
+        const bool store_ok = factive && (f0 + fl < a.n_frames);
+        const bool hasB = rowA + 1 < a.rows;
+        float* o0 = a.out + rowA * (long long)a.n_mels * a.n_frames + f0 + fl;
+        float* o1 = o0 + (long long)a.n_mels * a.n_frames;
+        const int4* steps = s_melh + warp * a.mel_steps_per_warp * 2;
+#pragma unroll 1
+        for (int st = 0; st < a.mel_steps_per_warp; ++st) {
+          const int4 h1 = steps[2 * st + 1];   // {n_iter (even), weight offset, first filter, filters in step}
+          if (h1.w == 0) break;
+          const int bin0 = reinterpret_cast<const int*>(steps + 2 * st)[q];
+          const float4* wq = s_melw + h1.y + q;
+          const float4* pp = pf + (bin0 >> 1);
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 2
+          for (int it = 0; it < h1.x; ++it) {
+            const float4 w = wq[4 * it];
+            const float4 p0 = pp[2 * it], p1 = pp[2 * it + 1];
+            acc = pfma(make_float2(p0.x, p0.y), w.x, acc);
+            acc = pfma(make_float2(p0.z, p0.w), w.y, acc);
+            acc = pfma(make_float2(p1.x, p1.y), w.z, acc);
+            acc = pfma(make_float2(p1.z, p1.w), w.w, acc);
+          }
+          if (store_ok && q < h1.w) {
+            const long long mo = (long long)((h1.z + q) * a.n_frames);
+            o0[mo] = acc.x;
+            if (hasB) o1[mo] = acc.y;
           }
         }
-      }
-    }
-    return;
-  } else {
-    // ---- power of every bin, kept in registers until the staging area is free ----------------
-    float2 pk[16], pq[16];   // 4|X[k]|^2 and 4|X[1024-k]|^2 for the two rows
-    float2 p512 = make_float2(0.f, 0.f);
-    if (fvalid) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        int ps = pshift - i;
-        ps = ps > 15 ? 15 : ps;
-        const float4 b = XB4r[ps * 32 + plane];
-        const float2 br = make_float2(b.x, b.y), bi = make_float2(b.z, b.w);
-        const float2 ar = re[i], ai = im[i];
-        const float2 t = __ldg(a.tw2 + lane + 32 * i);
-        const float2 e_r = padd(ar, br), e_i = psub(ai, bi);
-        const float2 o_r = padd(ai, bi), o_i = psub(br, ar);
-        const float2 xr = pfma(o_i, -t.y, pfma(o_r, t.x, e_r));   // Re(E2 + T)
-        const float2 xi = pfma(o_r, t.y, pfma(o_i, t.x, e_i));    // Im(E2 + T)
-        const float2 yr = pfma(o_i, t.y, pfma(o_r, -t.x, e_r));   // Re(E2 - T)
-        const float2 yi = pfma(o_r, -t.y, pfma(o_i, -t.x, e_i));  // Im(E2 - T)
-        pk[i] = pfma2(xi, xi, pmul(xr, xr));
-        pq[i] = pfma2(yi, yi, pmul(yr, yr));
-      }
-      if (lane == 0) {  // DC, Nyquist, bin 512
-        const float2 dc = padd(re[0], im[0]), ny = psub(re[0], im[0]);
-        pk[0] = pmuls(pmul(dc, dc), 4.f);
-        pq[0] = pmuls(pmul(ny, ny), 4.f);
-        p512 = pmuls(pfma2(im[16], im[16], pmul(re[16], re[16])), 4.f);
-      }
-    }
-    __syncthreads();  // every warp is done with its exchange buffer: the staging area becomes P
-    float* P = reinterpret_cast<float*>(stage);   // [8 (frame,row)][kPStride]
-    if (fvalid) {
-      float* p0 = P + (warp * 2 + 0) * kPStride;
-      float* p1 = P + (warp * 2 + 1) * kPStride;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int k = lane + 32 * i;
-        p0[k] = pk[i].x;
-        p1[k] = pk[i].y;
-        p0[1024 - k] = pq[i].x;
-        p1[1024 - k] = pq[i].y;
-      }
-      if (lane == 0) {
-        p0[512] = p512.x;
-        p1[512] = p512.y;
-        p0[1025] = p0[1026] = p0[1027] = 0.f;
-        p1[1025] = p1[1026] = p1[1027] = 0.f;
-      }
-    }
-    __syncthreads();
-
-    if constexpr (MODE == MODE_MEL) {
-      // lanes = 8 (frame,row) lines x 4 adjacent mel bins per warp; 16 bins per round
-      const int line = tid & 7;                 // frame = line>>1, row = line&1
-      const int fr = f0 + (line >> 1);
-      const long long row = rowA + (line & 1);
-      const bool ok = fr < a.n_frames && row < a.rows;
-      const float4* P4 = reinterpret_cast<const float4*>(P + line * kPStride);
-      for (int m = tid >> 3; m < a.n_mels; m += kThreads / 8) {
-        const int start4 = __ldg(a.mel_start4 + m) >> 2, cnt = __ldg(a.mel_cnt4 + m);
-        const float4* w4 = a.mel_w4 + __ldg(a.mel_off4 + m);
-        float acc0 = 0.f, acc1 = 0.f;
-        int j = 0;
-        for (; j + 1 < cnt; j += 2) {
-          const float4 p = P4[start4 + j], w = __ldg(w4 + j);
-          const float4 p2 = P4[start4 + j + 1], w2 = __ldg(w4 + j + 1);
-          acc0 = fmaf(p.x, w.x, acc0); acc1 = fmaf(p.y, w.y, acc1);
-          acc0 = fmaf(p.z, w.z, acc0); acc1 = fmaf(p.w, w.w, acc1);
-          acc0 = fmaf(p2.x, w2.x, acc0); acc1 = fmaf(p2.y, w2.y, acc1);
-          acc0 = fmaf(p2.z, w2.z, acc0); acc1 = fmaf(p2.w, w2.w, acc1);
-        }
-        if (j < cnt) {
-          const float4 p = P4[start4 + j], w = __ldg(w4 + j);
-          acc0 = fmaf(p.x, w.x, acc0); acc1 = fmaf(p.y, w.y, acc1);
-          acc0 = fmaf(p.z, w.z, acc0); acc1 = fmaf(p.w, w.w, acc1);
-        }
-        if (ok) a.out[(row * a.n_mels + m) * (long long)a.n_frames + fr] = acc0 + acc1;
-      }
-    } else {  // MODE_POWER: lanes = (8 bins) x (4 frames) -> 16-byte runs along the frame axis
-      const int fsub = tid & 3, ksub = (tid >> 2) & 7, grp = tid >> 5;
-      const int fr = f0 + fsub;
-      if (fr < a.n_frames) {
-        for (int r = 0; r < 2; ++r) {
-          if (rowA + r >= a.rows) break;
-          float* obase = a.out + (rowA + r) * (long long)a.n_freq * a.n_frames + fr;
-          const float* pl = P + (fsub * 2 + r) * kPStride;
-          for (int k = grp * 8 + ksub; k < 1025; k += 32) obase[(long long)k * a.n_frames] = 0.25f * pl[k];
+      } else {  // MODE_POWER: lanes = (32 bins) x (6 frames) -> 24-byte runs along the frame axis
+        const int fsub = tid % kWarps, ksub = tid / kWarps;
+        const int fr = f0 + fsub;
+        if (fr < a.n_frames) {
+          const bool hasB = rowA + 1 < a.rows;
+          float* o0 = a.out + rowA * (long long)a.n_freq * a.n_frames + fr;
+          float* o1 = o0 + (long long)a.n_freq * a.n_frames;
+          const float2* pl = P + fsub * kPLine;
+          for (int k = ksub; k < 1025; k += 32) {
+            const float2 v = pl[k];
+            o0[(long long)k * a.n_frames] = 0.25f * v.x;
+            if (hasB) o1[(long long)k * a.n_frames] = 0.25f * v.y;
+          }
         }
       }
     }
@@ -473,6 +593,10 @@ struct AaStftPlan {
   float2* d_tw2 = nullptr;
   int* d_mel_meta = nullptr;   // start4 | cnt4 | off4
   float4* d_mel_w4 = nullptr;
+  int4* d_mel_steps = nullptr;   // fast path mel step lists followed by the step weights
+  float* d_lane_consts = nullptr;
+  int mel_steps_per_warp = 0, mel_hdr_bytes = 0, mel_w_bytes = 0;
+  int fast_smem = 0, fast_grid_per_sm = 2;
   // resources of aa_stft_mel_f32_host (created lazily)
   cudaStream_t hstream[2] = {nullptr, nullptr};
   float* hbuf_in[2] = {nullptr, nullptr};
@@ -496,18 +620,33 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
   p->n_fft = n_fft; p->hop = hop; p->center = center ? 1 : 0; p->n_mels = n_mels; p->n_freq = n_fft / 2 + 1;
   const int M = n_fft / 2;
   while ((1 << p->log2m) < M) p->log2m++;
-  p->fast = (n_fft == 2048) && (hop % 4 == 0) && (hop <= 1024);
   AA_CUDA(cudaGetDevice(&p->device));
   const double PI = 3.14159265358979323846;
   // window as (w[2n], w[2n+1]) pairs
   std::vector<float> win(n_fft);
   for (int i = 0; i < n_fft; ++i)
     win[i] = window_host ? window_host[i] : (float)(0.5 - 0.5 * std::cos(2.0 * PI * i / n_fft));
+  bool is_hann = true;   // the fast kernel synthesises the periodic Hann window in registers
+  for (int i = 0; i < n_fft; ++i)
+    if (std::fabs(win[i] - (float)(0.5 - 0.5 * std::cos(2.0 * PI * i / n_fft))) > 2e-6f) { is_hann = false; break; }
+  p->fast = (n_fft == 2048) && (hop % 4 == 0) && (hop <= 1024) && is_hann;
   AA_CUDA(cudaMalloc(&p->d_window2, sizeof(float) * n_fft));
   AA_CUDA(cudaMemcpy(p->d_window2, win.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
   // twiddles
   std::vector<float2> tw1, tw2(std::max(n_fft / 4, 1) + 1);
   if (p->fast) {
+    std::vector<float> lc(32 * 4 + 32 * 2);
+    for (int l = 0; l < 32; ++l) {
+      for (int e = 0; e < 2; ++e) {
+        const double phi = 2.0 * PI * (double)(2 * l + e) / 2048.0;
+        lc[4 * l + 2 * e] = (float)std::cos(phi);
+        lc[4 * l + 2 * e + 1] = (float)std::sin(phi);
+      }
+      lc[128 + 2 * l] = (float)std::cos(2.0 * PI * l / 2048.0);
+      lc[128 + 2 * l + 1] = (float)(-std::sin(2.0 * PI * l / 2048.0));
+    }
+    AA_CUDA(cudaMalloc(&p->d_lane_consts, sizeof(float) * lc.size()));
+    AA_CUDA(cudaMemcpy(p->d_lane_consts, lc.data(), sizeof(float) * lc.size(), cudaMemcpyHostToDevice));
     tw1.resize(32 * 32);
     for (int k1 = 0; k1 < 32; ++k1)
       for (int n2 = 0; n2 < 32; ++n2) {
@@ -569,12 +708,71 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
     AA_CUDA(cudaMemcpy(p->d_mel_meta, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice));
     AA_CUDA(cudaMalloc(&p->d_mel_w4, sizeof(float) * w.size()));
     AA_CUDA(cudaMemcpy(p->d_mel_w4, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+    if (p->fast) {
+      // Step lists of the fused mel epilogue.  A step = 4 adjacent filters; its weight block is
+      // [n_iter][4 filters] float4 (4 bins each), n_iter = the longest filter of the step, shorter filters
+      // zero-padded; a filter whose padded range would leave the 1028-bin P line is shifted down.  Steps are
+      // dealt to the 6 warps longest-first onto the least loaded warp.
+      struct Step { int4 h0, h1; };
+      std::vector<Step> steps;
+      std::vector<float> sw;
+      for (int m0 = 0; m0 < n_mels; m0 += 4) {
+        const int nv = std::min(4, n_mels - m0);
+        int n_iter = 1;
+        for (int qq = 0; qq < nv; ++qq) n_iter = std::max(n_iter, meta[n_mels + m0 + qq]);
+        n_iter = (n_iter + 1) & ~1;   // the device loop is unrolled by two
+        AA_REQUIRE(4 * n_iter <= 1028, "mel filter too wide for the fused epilogue");
+        int bins[4] = {0, 0, 0, 0};
+        const int wofs = (int)(sw.size() / 4);
+        sw.resize(sw.size() + (size_t)n_iter * 16, 0.f);
+        for (int qq = 0; qq < nv; ++qq) {
+          const int m = m0 + qq, cnt = meta[n_mels + m];
+          int b0 = cnt > 0 ? meta[m] : 0;
+          const int shift = std::max(0, b0 + 4 * n_iter - 1028) / 4;   // groups to shift down
+          b0 -= 4 * shift;
+          bins[qq] = b0;
+          for (int c = 0; c < cnt; ++c)
+            for (int j = 0; j < 4; ++j)
+              sw[((size_t)wofs + (size_t)(c + shift) * 4 + qq) * 4 + j] = w[((size_t)meta[2 * n_mels + m] + c) * 4 + j];
+        }
+        steps.push_back({make_int4(bins[0], bins[1], bins[2], bins[3]), make_int4(n_iter, wofs, m0, nv)});
+      }
+      std::vector<int> order(steps.size()), load(kWarps, 0);
+      for (size_t i = 0; i < steps.size(); ++i) order[i] = (int)i;
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return steps[x].h1.x > steps[y].h1.x; });
+      std::vector<std::vector<int>> per_warp(kWarps);
+      for (int i : order) {
+        int best = 0;
+        for (int wq = 1; wq < kWarps; ++wq) if (load[wq] < load[best]) best = wq;
+        per_warp[best].push_back(i);
+        load[best] += steps[i].h1.x + 2;
+      }
+      size_t spw = 1;
+      for (auto& l : per_warp) spw = std::max(spw, l.size());
+      std::vector<int4> tab((size_t)kWarps * spw * 2, make_int4(0, 0, 0, 0));
+      for (int wq = 0; wq < kWarps; ++wq)
+        for (size_t i = 0; i < per_warp[wq].size(); ++i) {
+          tab[((size_t)wq * spw + i) * 2] = steps[per_warp[wq][i]].h0;
+          tab[((size_t)wq * spw + i) * 2 + 1] = steps[per_warp[wq][i]].h1;
+        }
+      p->mel_steps_per_warp = (int)spw;
+      p->mel_hdr_bytes = (int)(sizeof(int4) * tab.size());
+      p->mel_w_bytes = (int)(sizeof(float) * sw.size());
+      AA_CUDA(cudaMalloc(&p->d_mel_steps, p->mel_hdr_bytes + p->mel_w_bytes));
+      AA_CUDA(cudaMemcpy(p->d_mel_steps, tab.data(), p->mel_hdr_bytes, cudaMemcpyHostToDevice));
+      AA_CUDA(cudaMemcpy(reinterpret_cast<unsigned char*>(p->d_mel_steps) + p->mel_hdr_bytes, sw.data(), p->mel_w_bytes,
+                         cudaMemcpyHostToDevice));
+    }
   }
   if (p->fast) {
-    const int smem = (3 * hop + 2048) * 8 + kStageBytes + 16;
+    const int smem = ((kWarps - 1) * hop + 2048) * 8 + kStageBytes + kTableBytes + p->mel_hdr_bytes + p->mel_w_bytes + 32;
+    p->fast_smem = smem;
     AA_CUDA(cudaFuncSetAttribute(stft2048_kernel<MODE_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     AA_CUDA(cudaFuncSetAttribute(stft2048_kernel<MODE_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     AA_CUDA(cudaFuncSetAttribute(stft2048_kernel<MODE_MEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int nb = 0;
+    AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, stft2048_kernel<MODE_MEL>, kThreads, smem));
+    p->fast_grid_per_sm = std::max(1, nb);
   } else if (M * 12 + 64 > 48 * 1024) {
     const int smem = M * 12 + 64;
     AA_CUDA(cudaFuncSetAttribute(stft_generic_kernel<MODE_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -587,7 +785,7 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
 
 int aa_stft_plan_destroy(AaStftPlan* p) {
   if (!p) return AA_OK;
-  cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4);
+  cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4); cudaFree(p->d_mel_steps); cudaFree(p->d_lane_consts);
   for (int i = 0; i < 2; ++i) {
     if (p->hbuf_in[i]) cudaFree(p->hbuf_in[i]);
     if (p->hbuf_out[i]) cudaFree(p->hbuf_out[i]);
@@ -637,14 +835,19 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
   a.wav_aligned16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0) ? 1 : 0;
   if (p->fast) {
     a.tiles_per_pair = (int)((n_frames + kWarps - 1) / kWarps);
-    const int64_t pairs = (rows + 1) / 2, grid = pairs * a.tiles_per_pair;
-    AA_REQUIRE(grid < (1LL << 31), "grid too large (%lld tiles)", (long long)grid);
-    const int smem = (3 * p->hop + 2048) * 8 + kStageBytes + 16;
+    const int64_t pairs = (rows + 1) / 2;
+    a.n_tiles = pairs * a.tiles_per_pair;
+    a.mel_steps = p->d_mel_steps; a.mel_steps_per_warp = p->mel_steps_per_warp;
+    a.mel_hdr_bytes = p->mel_hdr_bytes; a.mel_w_bytes = p->mel_w_bytes; a.lane_consts = p->d_lane_consts;
+    AA_REQUIRE(a.n_tiles < (1LL << 31) && rows < (1LL << 30) && n_pad < (1LL << 30), "problem too large for the fast STFT path");
+    const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)p->fast_grid_per_sm * aa::num_sms());
+    const int smem = p->fast_smem;
     if (mode == MODE_COMPLEX) stft2048_kernel<MODE_COMPLEX><<<(unsigned)grid, kThreads, smem, st>>>(a);
     else if (mode == MODE_POWER) stft2048_kernel<MODE_POWER><<<(unsigned)grid, kThreads, smem, st>>>(a);
     else stft2048_kernel<MODE_MEL><<<(unsigned)grid, kThreads, smem, st>>>(a);
   } else {
-    a.tiles_per_pair = 0;
+    a.tiles_per_pair = 0; a.n_tiles = 0; a.mel_steps = nullptr; a.mel_steps_per_warp = 0;
+    a.mel_hdr_bytes = a.mel_w_bytes = 0; a.lane_consts = nullptr;
     const int64_t grid = rows * n_frames;
     AA_REQUIRE(grid < (1LL << 31), "grid too large (%lld frames)", (long long)grid);
     const int M = p->n_fft / 2, smem = M * 12 + 64;

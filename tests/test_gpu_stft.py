@@ -101,6 +101,16 @@ def test_oracle_sweep(aab, n_fft, hop, n):
                   O.mel_spectrogram(x, 48000, n_fft, hop, n_mels=64)) < TOL
 
 
+def test_custom_window_uses_the_table_path(aab):
+    "a non-Hann window_fn (torchaudio kwarg) must not go through the Hann-synthesising fast kernel"
+    O = _oracle()
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(2, 2, 8192, generator=g) - 0.5
+    w = torch.hamming_window(2048)
+    out = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512, window_fn=torch.hamming_window).encode(x.cuda())
+    assert rel_l2(out, O.mel_spectrogram(x, 48000, 2048, 512, window=w.double())) < TOL
+
+
 def test_center_false_and_no_zero_pad(aab):
     O = _oracle()
     g = torch.Generator().manual_seed(5)
