@@ -9,3 +9,6 @@ __version__ = "0.1.0"
 from . import _lib  # noqa: F401  (loads libaa_b200.so or raises)
 from .given_models import (GivenModelClass, SpectrogramAE, MagSpectrogramAE, MagDPhaseSpectrogramAE,  # noqa: F401
                            MelSpectrogramAE)
+from .aa_mixer import (EmbedBlock, AudioAlgebra, get_stems_faders, do_mixing, mseloss, vicreg_var_loss,  # noqa: F401
+                       vicreg_var_loss_l2, vicreg_cov_loss, off_diagonal, latent_lincomb)
+from . import aa_mixer, aa_effects, latent_ops, pca, given_models  # noqa: F401

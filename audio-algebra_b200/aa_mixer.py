@@ -1,0 +1,357 @@
+"""AA core of the reference's audio_algebra/aa_mixer.py with the same names and call contracts:
+EmbedBlock, AudioAlgebra, get_stems_faders, do_mixing, mseloss, vicreg_var_loss, vicreg_cov_loss,
+off_diagonal -- computed by libaa_b200 kernels (fused projector halves, Gram-identity covariance loss,
+deterministic two-stage reductions) with torch.autograd.Function wrappers for training.
+
+Mirrors /root/reference/audio_algebra/aa_mixer.py:205-364 (and the copies in aa_effects.py:51-162,
+train_aa_mixer_accel.py:274-460).  Tensors must live on a B200; there is no CPU path.
+"""
+import ctypes as C
+import random
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+__all__ = ['EmbedBlock', 'AudioAlgebra', 'get_stems_faders', 'do_mixing', 'mseloss', 'vicreg_var_loss',
+           'vicreg_cov_loss', 'off_diagonal', 'latent_lincomb']
+
+_p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_pp = C.POINTER(C.c_void_p)
+_lib.register({
+    "aa_latent_lincomb_f32": (_i, [_i, _pp, C.POINTER(_f), _p, _i64, _p]),
+    "aa_latent_unary_f32": (_i, [_i, _p, _p, _i64, _i64, _i64, _f, _p, _p]),
+    "aa_effect_transfer_f32": (_i, [_p, _i64, _p, _p, _i64, _i64, _p, _p]),
+    "aa_reduce_workspace_floats": (_i64, []),
+    "aa_mse_fwd_f32": (_i, [_p, _p, _i64, _p, _p, _p]),
+    "aa_mse_bwd_f32": (_i, [_p, _p, _i64, _p, _f, _p, _p, _i, _p]),
+    "aa_vicreg_var_fwd_f32": (_i, [_p, _i64, _i64, _f, _f, _i, _p, _p, _p, _p]),
+    "aa_vicreg_var_bwd_f32": (_i, [_p, _p, _i64, _i64, _f, _f, _i, _p, _f, _p, _i, _p]),
+    "aa_cov_loss_workspace_floats": (_i64, [_i64, _i64]),
+    "aa_vicreg_cov_fwd_f32": (_i, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "aa_vicreg_cov_bwd_f32": (_i, [_p, _p, _p, _i64, _i64, _p, _f, _p, _i, _p]),
+    "aa_projector_half_fwd_f32": (_i, [_pp, _pp, _i, _i, _i, _p, _i64, _i64, _p, _p]),
+    "aa_projector_bwd_workspace_floats": (_i64, []),
+    "aa_projector_half_bwd_f32": (_i, [_pp, _pp, _i, _i, _i, _p, _p, _i64, _i64, _p, _i, _pp, _pp, _i, _f, _p, _p]),
+    "aa_cov_workspace_floats": (_i64, [_i64]),
+    "aa_cov_accumulate_f32": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "aa_adam_step_f32": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _p]),
+})
+
+_RED_WS = int(lib.aa_reduce_workspace_floats())
+
+
+def _f32c(t: Tensor, what="tensor") -> Tensor:
+    _lib.require_cuda(t, what)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+    return C.cast(arr, _pp), arr  # keep `arr` alive while the call runs
+
+
+def _ws(n, device):
+    return torch.empty(int(n), dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------
+# latent algebra
+# ---------------------------------------------------------------------------------------------------
+
+def latent_lincomb(zs, coeffs, out=None) -> Tensor:
+    "sum_j coeffs[j] * zs[j] in one pass (zsum, effect guesses zb2 - zb1 + za1, z + diff, ...)"
+    zs = [_f32c(z) for z in zs]
+    assert 1 <= len(zs) <= 8 and len(zs) == len(coeffs)
+    n = zs[0].numel()
+    assert all(z.numel() == n for z in zs)
+    if out is None:
+        out = torch.empty_like(zs[0])
+    pa, keep = _ptr_array(zs)
+    ca = (C.c_float * len(zs))(*[float(c) for c in coeffs])
+    with torch.cuda.device(zs[0].device):
+        check(lib.aa_latent_lincomb_f32(len(zs), pa, ca, ptr(out), n, stream_ptr()))
+    return out
+
+
+class _LinComb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coeffs, *zs):
+        ctx.coeffs = coeffs
+        return latent_lincomb([z.detach() for z in zs], coeffs)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(g * c if c != 1.0 else g for c in ctx.coeffs)
+
+
+def _lincomb_ad(zs, coeffs):
+    return _LinComb.apply(tuple(float(c) for c in coeffs), *zs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------
+
+class _MSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _f32c(a, "mseloss input"), _f32c(b, "mseloss target")
+        assert a.shape == b.shape, f"mseloss: shapes differ {a.shape} vs {b.shape}"
+        loss = torch.empty((), dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            check(lib.aa_mse_fwd_f32(ptr(a), ptr(b), a.numel(), ptr(loss), ptr(_ws(_RED_WS, a.device)), stream_ptr()))
+        ctx.save_for_backward(a, b)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous().float()
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(a.device):
+            check(lib.aa_mse_bwd_f32(ptr(a), ptr(b), a.numel(), ptr(g), 1.0,
+                                     None if ga is None else ptr(ga), None if gb is None else ptr(gb), 0, stream_ptr()))
+        return ga, gb
+
+
+def mseloss(a: Tensor, b: Tensor) -> Tensor:
+    "nn.MSELoss() (aa_mixer.py:344): mean((a-b)^2)"
+    return _MSE.apply(a, b)
+
+
+class _VarLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, gamma, eps, l2):
+        z = _f32c(z, "z")
+        b, d = z.shape[0], z.numel() // z.shape[0]
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        stats = torch.empty((2, d), dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            check(lib.aa_vicreg_var_fwd_f32(ptr(z), b, d, float(gamma), float(eps), int(l2), ptr(loss), ptr(stats),
+                                            ptr(_ws(max(_RED_WS, (d + 255) // 256), z.device)), stream_ptr()))
+        ctx.save_for_backward(z, stats)
+        ctx.cfg = (b, d, float(gamma), float(eps), int(l2))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        z, stats = ctx.saved_tensors
+        b, d, gamma, eps, l2 = ctx.cfg
+        gz = torch.empty_like(z)
+        g = g.contiguous().float()
+        with torch.cuda.device(z.device):
+            check(lib.aa_vicreg_var_bwd_f32(ptr(z), ptr(stats), b, d, gamma, eps, l2, ptr(g), 1.0, ptr(gz), 0, stream_ptr()))
+        return gz, None, None, None
+
+
+def vicreg_var_loss(z: Tensor, gamma=1, eps=1e-4) -> Tensor:
+    "aa_mixer.py:351-353: mean(relu(gamma - sqrt(z.var(dim=0) + eps)))"
+    return _VarLoss.apply(z, gamma, eps, False)
+
+
+def vicreg_var_loss_l2(z: Tensor, gamma=1, eps=1e-4) -> Tensor:
+    "train_aa_effects.py:42-44: mean(relu(gamma - std)**2)"
+    return _VarLoss.apply(z, gamma, eps, True)
+
+
+def off_diagonal(x: Tensor) -> Tensor:
+    "aa_mixer.py:355-358 (kept for API compatibility; the CUDA covariance loss never builds the matrix)"
+    n, m = x.shape
+    assert n == m
+    return x.flatten()[:-1].view(n - 1, n + 1)[:, 1:].flatten()
+
+
+class _CovLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        z = _f32c(z, "z")
+        b, d = z.shape[0], z.numel() // z.shape[0]
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        stats = torch.empty((2, d), dtype=torch.float32, device=z.device)
+        gram = torch.empty((b, b), dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            ws = _ws(lib.aa_cov_loss_workspace_floats(b, d), z.device)
+            check(lib.aa_vicreg_cov_fwd_f32(ptr(z), b, d, None, ptr(stats), ptr(gram), ptr(loss), ptr(ws), stream_ptr()))
+        ctx.save_for_backward(z, stats, gram)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        z, stats, gram = ctx.saved_tensors
+        b, d = z.shape[0], z.numel() // z.shape[0]
+        gz = torch.empty_like(z)
+        g = g.contiguous().float()
+        with torch.cuda.device(z.device):
+            check(lib.aa_vicreg_cov_bwd_f32(ptr(z), ptr(stats), ptr(gram), b, d, ptr(g), 1.0, ptr(gz), 0, stream_ptr()))
+        return gz
+
+
+def vicreg_cov_loss(z: Tensor) -> Tensor:
+    """aa_mixer.py:360-364: sum of squared off-diagonal entries of cov(z as [(c t), b]) / (c t).
+    Computed through the B x B Gram matrix (identical scalar, no (C T)^2 matrix)."""
+    return _CovLoss.apply(z)
+
+
+# ---------------------------------------------------------------------------------------------------
+# projector
+# ---------------------------------------------------------------------------------------------------
+
+class _ProjHalf(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, resid, dims, hidden, *wb):
+        x = _f32c(x, "projector input")
+        assert x.dim() == 3 and x.shape[1] == dims, f"expected [B,{dims},T], got {tuple(x.shape)}"
+        ws, bs = [_f32c(w) for w in wb[:4]], [_f32c(b) for b in wb[4:]]
+        out = torch.empty_like(x)
+        wp, k1 = _ptr_array(ws)
+        bp, k2 = _ptr_array(bs)
+        with torch.cuda.device(x.device):
+            check(lib.aa_projector_half_fwd_f32(wp, bp, dims, hidden, int(resid), ptr(x), x.shape[0], x.shape[2], ptr(out),
+                                                stream_ptr()))
+        ctx.save_for_backward(x, *ws, *bs)
+        ctx.cfg = (bool(resid), dims, hidden)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *wb = ctx.saved_tensors
+        ws, bs = wb[:4], wb[4:]
+        resid, dims, hidden = ctx.cfg
+        g = _f32c(g)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gws, gbs = [torch.empty_like(w) for w in ws], [torch.empty_like(b) for b in bs]
+        wp, k1 = _ptr_array(ws)
+        bp, k2 = _ptr_array(bs)
+        gwp, k3 = _ptr_array(gws)
+        gbp, k4 = _ptr_array(gbs)
+        with torch.cuda.device(x.device):
+            wsb = _ws(lib.aa_projector_bwd_workspace_floats(), x.device)
+            check(lib.aa_projector_half_bwd_f32(wp, bp, dims, hidden, int(resid), ptr(x), ptr(g), x.shape[0], x.shape[2],
+                                                None if gx is None else ptr(gx), 0, gwp, gbp, 0, 1.0, ptr(wsb), stream_ptr()))
+        return (gx, None, None, None, *gws, *gbs)
+
+
+class EmbedBlock(nn.Module):
+    """Parameter holder with the reference's layout (aa_mixer.py:205-221): `lin` = nn.Linear(in, out).
+    The arithmetic of four consecutive blocks is fused in AudioAlgebra.encode/decode; calling a single
+    block directly is not part of the accelerated path."""
+
+    def __init__(self, in_dims: int, out_dims: int, act=nn.GELU(), resid=True, use_bn=False, requires_grad=True, **kwargs) -> None:
+        super().__init__()
+        if use_bn:
+            raise NotImplementedError("use_bn=True is not supported by the fused projector")
+        if act is not None and not (isinstance(act, nn.GELU) and getattr(act, "approximate", "none") == "none"):
+            raise NotImplementedError("the fused projector implements act=nn.GELU() (exact erf) or act=None")
+        self.in_dims, self.out_dims, self.act, self.resid = in_dims, out_dims, act, resid
+        self.lin = nn.Linear(in_dims, out_dims, **kwargs)
+        self.bn = None
+        if requires_grad == False:  # noqa: E712  (reference spelling)
+            self.lin.weight.requires_grad = False
+            self.lin.bias.requires_grad = False
+
+    def forward(self, xin: Tensor) -> Tensor:
+        raise NotImplementedError("EmbedBlock is evaluated inside AudioAlgebra.encode/decode (fused kernel)")
+
+
+class AudioAlgebra(nn.Module):
+    """Main AudioAlgebra model (aa_mixer.py:224-267): encode(x) = x + enc(x^T)^T, decode likewise,
+    forward -> (z, decode(z)); x is [B, dims, T].  state_dict keys match the reference
+    (encoder.{0..3}.lin.{weight,bias}, decoder.{0..3}.lin.{weight,bias})."""
+
+    def __init__(self, dims=32, hidden_dims=64, act=nn.GELU(), use_bn=False, resid=True, block=EmbedBlock, trivial=False):
+        super().__init__()
+        if block is not EmbedBlock:
+            raise NotImplementedError("custom block classes are not supported by the fused projector")
+        if dims > 64 or hidden_dims > 64:
+            raise NotImplementedError("the fused projector supports dims, hidden_dims <= 64")
+        self.resid, self.trivial, self.dims, self.hidden_dims = resid, trivial, dims, hidden_dims
+        self.encoder = nn.Sequential(
+            block(dims, hidden_dims, act=act, use_bn=use_bn, resid=resid),
+            block(hidden_dims, hidden_dims, act=act, use_bn=use_bn, resid=resid),
+            block(hidden_dims, hidden_dims, act=act, use_bn=use_bn, resid=resid),
+            block(hidden_dims, dims, act=None, use_bn=use_bn, resid=resid),
+        )
+        self.decoder = nn.Sequential(
+            block(dims, hidden_dims, act=act, use_bn=use_bn, resid=resid),
+            block(hidden_dims, hidden_dims, act=act, use_bn=use_bn, resid=resid),
+            block(hidden_dims, hidden_dims, act=act, use_bn=use_bn, resid=resid),
+            block(hidden_dims, dims, act=None, use_bn=use_bn, resid=resid),
+        )
+
+    def _half(self, seq, xin):
+        ws = [blk.lin.weight for blk in seq]
+        bs = [blk.lin.bias for blk in seq]
+        return _ProjHalf.apply(xin, self.resid, self.dims, self.hidden_dims, *ws, *bs)
+
+    def encode(self, xin):
+        if self.trivial:
+            return xin
+        return self._half(self.encoder, xin)
+
+    def decode(self, xin):
+        if self.trivial:
+            return xin
+        return self._half(self.decoder, xin)
+
+    def forward(self, x):
+        xprime = self.encode(x)
+        xprimeprime = self.decode(xprime)
+        return xprime, xprimeprime
+
+
+# ---------------------------------------------------------------------------------------------------
+# stems / faders / mixing
+# ---------------------------------------------------------------------------------------------------
+
+def get_stems_faders(batch, dl_iter, dl, maxstems=2, unity_gain=False, debug=False):
+    "aa_mixer.py:270-292, same RNG recipe (python `random` for nstems, torch CPU RNG for the faders)"
+    nstems = random.randint(2, maxstems)
+    if debug:
+        print("maxstems, nstems =", maxstems, nstems)
+    device = batch.device
+    faders = torch.sgn(2 * torch.rand(nstems) - 1)
+    if not unity_gain:
+        faders += 0.5 * torch.tanh(2 * (2 * torch.rand(nstems) - 1))
+    stems = [batch]
+    for i in range(nstems - 1):
+        try:
+            next_stem = next(dl_iter).to(device)
+        except StopIteration:
+            dl_iter = iter(dl)
+            next_stem = next(dl_iter).to(device)
+        if debug:
+            print("  next_stem.shape = ", next_stem.shape)
+        stems.append(next_stem)
+    return stems, faders.to(device), dl_iter
+
+
+def do_mixing(stems, faders, given_model, aa_model, device, debug=False, **kwargs):
+    """aa_mixer.py:295-327.  Same outputs (zsum, zmix, archive).  The reference re-encodes the running
+    mix after every stem and keeps only the last result; here the mix is encoded once after the loop
+    (identical zmix / archive['ymix'])."""
+    zs, ys, fadedstems, yrecons = [], [], [], []
+    fl = [float(f) for f in (faders.detach().cpu().tolist() if torch.is_tensor(faders) else faders)]
+    stems = [s.to(device) for s in stems]
+    for s, f in zip(stems, fl):
+        fadedstem = latent_lincomb([s], [f])
+        with torch.no_grad():
+            y = given_model.encode(fadedstem)
+        z, y_recon = aa_model(y)
+        yrecons.append(y_recon); zs.append(z); ys.append(y); fadedstems.append(fadedstem)
+    n = len(zs)
+    zsum = _lincomb_ad(zs, [1.0] * n) if n > 1 else zs[0]
+    mix = latent_lincomb(stems[:n], fl[:n])
+    with torch.no_grad():
+        ymix = given_model.encode(mix)
+        ysum = latent_lincomb(ys, [1.0] * n) if n > 1 else ys[0]
+    zmix, ymix_recon = aa_model(ymix)
+    archive = {'zs': zs, 'mix': mix, 'ys': ys, 'ymix': ymix, 'ymix_recon': ymix_recon, 'fadedstems': fadedstems,
+               'yrecons': yrecons, 'ysum': ysum}
+    return zsum, zmix, archive

@@ -438,8 +438,9 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
         const float4* pf = reinterpret_cast<const float4*>(P + (factive ? fl : 0) * kPLine);
         const bool store_ok = factive && (f0 + fl < a.n_frames);
         const bool hasB = rowA + 1 < a.rows;
-        float* o0 = a.out + rowA * (long long)a.n_mels * a.n_frames + f0 + fl;
-        float* o1 = o0 + (long long)a.n_mels * a.n_frames;
+        // 32-bit output indexing (the host routes outputs of >= 2^31 elements to the generic kernel)
+        const int plane_sz = a.n_mels * a.n_frames;
+        const int obase = (int)rowA * plane_sz + f0 + fl;
         const int4* steps = s_melh + warp * a.mel_steps_per_warp * 2;
 #pragma unroll 1
         for (int st = 0; st < a.mel_steps_per_warp; ++st) {
@@ -459,9 +460,9 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
             acc = pfma(make_float2(p1.z, p1.w), w.w, acc);
           }
           if (store_ok && q < h1.w) {
-            const long long mo = (long long)((h1.z + q) * a.n_frames);
-            o0[mo] = acc.x;
-            if (hasB) o1[mo] = acc.y;
+            const int idx = obase + (h1.z + q) * a.n_frames;
+            a.out[idx] = acc.x;
+            if (hasB) a.out[idx + plane_sz] = acc.y;
           }
         }
       } else {  // MODE_POWER: lanes = (32 bins) x (6 frames) -> 24-byte runs along the frame axis
@@ -833,7 +834,8 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
   a.mel_off4 = p->d_mel_meta ? p->d_mel_meta + 2 * p->n_mels : nullptr;
   a.mel_w4 = p->d_mel_w4; a.out = out;
   a.wav_aligned16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0) ? 1 : 0;
-  if (p->fast) {
+  const bool big_out = rows * (int64_t)std::max(p->n_freq, p->n_mels) * n_frames >= (1LL << 31);
+  if (p->fast && !big_out) {
     a.tiles_per_pair = (int)((n_frames + kWarps - 1) / kWarps);
     const int64_t pairs = (rows + 1) / 2;
     a.n_tiles = pairs * a.tiles_per_pair;

@@ -1,0 +1,108 @@
+"""Mixer training step of the reference's train_aa_mixer_accel.py:463-550 on B200: same loss recipe,
+Adam(lr=5e-4) + OneCycleLR(max_lr=1e-3) semantics (including OneCycleLR's default beta1 cycling), one
+flat fp32 parameter / gradient buffer, fused Adam kernel, and a *real* gradient all-reduce over
+torch.distributed (the reference's accelerate script bypasses DDP.forward and never synchronises
+gradients -- SURVEY.md section 5)."""
+import math
+
+import torch
+
+from ._lib import lib, check, ptr, stream_ptr
+from .aa_mixer import (AudioAlgebra, do_mixing, get_stems_faders, mseloss, vicreg_var_loss, vicreg_cov_loss)  # noqa: F401
+
+__all__ = ['FlatAdam', 'onecycle_lr', 'onecycle_beta1', 'mixer_losses', 'MixerTrainer']
+
+
+def _cos(a, b, pct):
+    return b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1)
+
+
+def onecycle_lr(step, total_steps, max_lr=1e-3, pct_start=0.3, div_factor=25.0, final_div_factor=1e4):
+    "lr used by optimiser step `step` (0-based) under torch's OneCycleLR defaults"
+    initial, min_lr = max_lr / div_factor, max_lr / div_factor / final_div_factor
+    up_end, down_end = float(pct_start * total_steps) - 1, total_steps - 1
+    if step <= up_end:
+        return _cos(initial, max_lr, step / up_end)
+    return _cos(max_lr, min_lr, (step - up_end) / (down_end - up_end))
+
+
+def onecycle_beta1(step, total_steps, pct_start=0.3, base_momentum=0.85, max_momentum=0.95):
+    up_end, down_end = float(pct_start * total_steps) - 1, total_steps - 1
+    if step <= up_end:
+        return _cos(max_momentum, base_momentum, step / up_end)
+    return _cos(base_momentum, max_momentum, (step - up_end) / (down_end - up_end))
+
+
+class FlatAdam:
+    "torch.optim.Adam + OneCycleLR on one flat fp32 CUDA buffer, one kernel per step"
+
+    def __init__(self, flat_params, lr=5e-4, max_lr=1e-3, total_steps=None, betas=(0.9, 0.999), eps=1e-8):
+        assert flat_params.is_cuda and flat_params.dtype == torch.float32 and flat_params.is_contiguous()
+        self.params = flat_params
+        self.m = torch.zeros_like(flat_params)
+        self.v = torch.zeros_like(flat_params)
+        self.lr, self.max_lr, self.total_steps, self.betas, self.eps = lr, max_lr, total_steps, betas, eps
+        self.t = 0
+
+    def current_lr(self):
+        return self.lr if self.total_steps is None else onecycle_lr(self.t, self.total_steps, self.max_lr)
+
+    def step(self, flat_grads):
+        lr = self.current_lr()
+        b1 = self.betas[0] if self.total_steps is None else onecycle_beta1(self.t, self.total_steps)
+        self.t += 1
+        with torch.cuda.device(self.params.device):
+            check(lib.aa_adam_step_f32(ptr(self.params), ptr(flat_grads.contiguous()), ptr(self.m), ptr(self.v),
+                                       self.params.numel(), lr, b1, self.betas[1], self.eps, self.t, stream_ptr()))
+
+
+def mixer_losses(zsum, zmix, y, yrecon, ymix, ymix_recon):
+    "train_aa_mixer_accel.py:504-517"
+    mix_loss = mseloss(zsum, zmix)
+    var_loss = (vicreg_var_loss(zsum) + vicreg_var_loss(zmix)) / 2
+    cov_loss = (vicreg_cov_loss(zsum) + vicreg_cov_loss(zmix)) / 2
+    aa_recon_loss = mseloss(y, yrecon) + mseloss(ymix, ymix_recon)
+    loss = mix_loss + var_loss + cov_loss + aa_recon_loss
+    return {'loss': loss, 'mix_loss': mix_loss, 'var_loss': var_loss, 'cov_loss': cov_loss, 'aa_recon_loss': aa_recon_loss}
+
+
+class MixerTrainer:
+    """One data-parallel rank of the mixer training loop.  Parameters of `aa_model` are re-pointed into a
+    flat buffer so that the gradient all-reduce is ONE 133 KB message and Adam is one kernel."""
+
+    def __init__(self, given_model, aa_model, total_steps, lr=5e-4, max_lr=1e-3, process_group=None):
+        import torch.distributed as dist
+        self.given_model, self.aa_model, self.group = given_model, aa_model, process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        params = [p for p in aa_model.parameters()]
+        self.flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+        self.flat_grad = torch.zeros_like(self.flat)
+        off = 0
+        for p in params:  # parameters and their .grad become views of the flat buffers
+            n = p.numel()
+            p.data = self.flat[off:off + n].view_as(p)
+            p.grad = self.flat_grad[off:off + n].view_as(p)
+            off += n
+        self.opt = FlatAdam(self.flat, lr=lr, max_lr=max_lr, total_steps=total_steps)
+
+    def step(self, stems, faders, batch=None):
+        """stems: list of [B,2,N] device tensors (stems[0] doubles as `batch` of the reference loop);
+        returns the dict of (detached, on-device) loss terms -- no host sync."""
+        import torch.distributed as dist
+        self.flat_grad.zero_()
+        device = stems[0].device
+        zsum, zmix, archive = do_mixing(stems, faders, self.given_model, self.aa_model, device)
+        with torch.no_grad():
+            y = archive['ys'][0] if batch is None else self.given_model.encode(batch)
+        # the reference re-encodes `batch` un-faded; with batch given we follow it exactly
+        if batch is None:
+            with torch.no_grad():
+                y = self.given_model.encode(stems[0])
+        z, yrecon = self.aa_model(y)
+        losses = mixer_losses(zsum, zmix, y, yrecon, archive['ymix'], archive['ymix_recon'])
+        losses['loss'].backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, group=self.group)
+            self.flat_grad.div_(self.world)
+        self.opt.step(self.flat_grad)
+        return {k: v.detach() for k, v in losses.items()}

@@ -128,12 +128,31 @@ int aa_vicreg_var_bwd_f32(const float* z, const float* stats, int64_t b, int64_t
  * instead of materialising the DxD covariance (aa_mixer.py:360-364).  gram: [B][B] f32 scratch that
  * also feeds the backward; stats as produced by aa_vicreg_var_fwd_f32 (or NULL: computed internally
  * into `stats_out`, [2][D]). */
+/* workspace for aa_vicreg_cov_fwd_f32: >= aa_cov_loss_workspace_floats(b, d) floats */
+int64_t aa_cov_loss_workspace_floats(int64_t b, int64_t d);
 int aa_vicreg_cov_fwd_f32(const float* z, int64_t b, int64_t d, const float* stats, float* stats_out,
                           float* gram, float* loss, float* workspace, void* stream);
 /* grad_z (+)= gscale * dL/dz,  dL/dX = 4/((B-1)^2 D) (G X - X diag(s)), s_d = sum_b X_bd^2, projected
  * onto zero-mean columns. */
 int aa_vicreg_cov_bwd_f32(const float* z, const float* stats, const float* gram, int64_t b, int64_t d,
                           const float* gloss, float gscale, float* grad_z, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Projector (aa_mixer.py:205-267): one half (encode or decode) of AudioAlgebra =
+ *   4 EmbedBlocks (Linear + exact-erf GELU on the first three, inner residual iff in==out) applied to
+ *   x^T, transposed back, plus the outer residual -- fused in one kernel on the channel-major tensor.
+ * x, out: [B][dims][T] f32.  w_host / b_host: host arrays of 4 device pointers, nn.Linear layout
+ * ([out][in], [out]) with shapes dims->hidden, hidden->hidden, hidden->hidden, hidden->dims; dims, hidden <= 64.
+ * ------------------------------------------------------------------------------------------ */
+int aa_projector_half_fwd_f32(const float* const* w_host, const float* const* b_host, int dims, int hidden, int resid,
+                              const float* x, int64_t batch, int64_t t, float* out, void* stream);
+int64_t aa_projector_bwd_workspace_floats(void);
+/* Backward of the same half: recomputes the activations from x.  gx (+)= dL/dx (may be NULL);
+ * gw_host[l] / gb_host[l] (+)= gscale * dL/dW_l, dL/db_l (deterministic two-stage reduction). */
+int aa_projector_half_bwd_f32(const float* const* w_host, const float* const* b_host, int dims, int hidden, int resid,
+                              const float* x, const float* gout, int64_t batch, int64_t t, float* gx, int accumulate_gx,
+                              float* const* gw_host, float* const* gb_host, int accumulate_gw, float gscale,
+                              float* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * PCA accumulation (calc_effects_pca.py:81-89): y [B][C][T] f32 -> cov_num [C][C] += C-by-C

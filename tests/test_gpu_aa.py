@@ -1,0 +1,279 @@
+"""GPU parity of the AA core (projector, latent algebra, losses, mixing, PCA, Adam) against fixtures
+from the reference's own code (tests/golden) and the float64 oracle.  Tolerances: fp32 kernels,
+relative L2 <= 1e-3 on embeddings (BASELINE.json); most checks are much tighter."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def aab():
+    import audio_algebra_b200 as aab
+    return aab
+
+
+def _oracle():
+    from oracle import aa_oracle as O
+    return O
+
+
+def _load_aa(aab, g, prefix="sd.", dims=64, hidden=64):
+    m = aab.AudioAlgebra(dims=dims, hidden_dims=hidden)
+    m.load_state_dict({k[len(prefix):]: T(v) for k, v in g.items() if k.startswith(prefix)})
+    return m.cuda()
+
+
+def test_projector_forward_golden(aab, golden):
+    g = golden("projector")
+    aa = _load_aa(aab, g)
+    y = T(g["y"]).cuda()
+    z, yr = aa(y)
+    assert rel_l2(z, g["z"]) < 1e-5 and rel_l2(yr, g["y_recon"]) < 1e-5
+    assert rel_l2(aa.encode(y), g["z_encode"]) < 1e-5
+    assert rel_l2(aa.decode(y), g["y_decode_of_y"]) < 1e-5
+    # state_dict layout is the reference's
+    assert set(aa.state_dict()) == {k[3:] for k in g if k.startswith("sd.")}
+
+
+def test_projector_toy_dims(aab, golden):
+    g = golden("projector")
+    aa = _load_aa(aab, g, "toy_sd.", 2, 16)
+    z, yr = aa(T(g["toy_y"]).cuda())
+    assert rel_l2(z, g["toy_z"]) < 1e-5 and rel_l2(yr, g["toy_y_recon"]) < 1e-5
+
+
+def test_projector_backward_golden(aab, golden):
+    g = golden("projector")
+    aa = _load_aa(aab, g)
+    y = T(g["y"]).cuda().requires_grad_(True)
+    z, yr = aa(y)
+    ((z * T(g["gz"]).cuda()).sum() + (yr * T(g["gyr"]).cuda()).sum()).backward()
+    assert rel_l2(y.grad, g["grad_y"]) < 1e-4
+    for k, p in aa.named_parameters():
+        assert rel_l2(p.grad, g["grad." + k]) < 1e-4, k
+
+
+def test_projector_ragged_and_large(aab):
+    "T not a multiple of the 32-token tile; many tiles per CTA; compared with the float64 oracle"
+    O = _oracle()
+    sd = O.init_projector_state_dict(64, 64, seed=2)
+    aa = aab.AudioAlgebra(64, 64)
+    aa.load_state_dict(sd)
+    aa = aa.cuda()
+    ew, eb, dw, db = O.projector_params_from_state_dict(sd)
+    g = torch.Generator().manual_seed(3)
+    for shape in [(1, 64, 1), (2, 64, 37), (40, 64, 515)]:
+        y = torch.randn(*shape, generator=g)
+        z, yr = aa(y.cuda())
+        zo, yro = O.projector_forward(y.double(), ew, eb, dw, db)
+        assert rel_l2(z, zo) < 1e-5 and rel_l2(yr, yro) < 1e-5
+    # gradient check at a ragged size
+    y = torch.randn(5, 64, 70, generator=g)
+    gz = torch.randn(5, 64, 70, generator=g)
+    yc = y.cuda().requires_grad_(True)
+    aa.zero_grad()
+    z, yr = aa(yc)
+    (z * gz.cuda()).sum().backward()
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    ew, eb, dw, db = O.projector_params_from_state_dict(sdd)
+    yd = y.double().requires_grad_(True)
+    zo, _ = O.projector_forward(yd, ew, eb, dw, db)
+    (zo * gz.double()).sum().backward()
+    assert rel_l2(yc.grad, yd.grad) < 1e-4
+    for k, p in aa.named_parameters():
+        if k.startswith("encoder"):
+            assert rel_l2(p.grad, sdd[k].grad) < 1e-4, k
+    assert aa.decoder[0].lin.weight.grad is None or float(aa.decoder[0].lin.weight.grad.abs().max()) == 0.0
+
+
+def test_losses_golden(aab, golden):
+    g = golden("losses")
+    za, zb = T(g["za"]).cuda(), T(g["zb"]).cuda()
+    assert abs(aab.mseloss(za, zb).item() - g["mse"]) < 1e-5 * abs(g["mse"])
+    assert abs(aab.vicreg_var_loss(za).item() - g["var_a"]) < 1e-4 * max(abs(g["var_a"]), 1e-3)
+    assert abs(aab.vicreg_var_loss(0.2 * zb).item() - g["var_b_small"]) < 1e-5 * abs(g["var_b_small"])
+    assert abs(aab.vicreg_var_loss_l2(0.2 * zb).item() - g["var_b_small_l2"]) < 1e-5 * abs(g["var_b_small_l2"])
+    assert abs(aab.vicreg_cov_loss(za).item() - g["cov_a"]) < 1e-4 * abs(g["cov_a"])
+    assert abs(aab.vicreg_cov_loss(zb).item() - g["cov_b"]) < 1e-4 * abs(g["cov_b"])
+
+
+def test_loss_gradients_golden(aab, golden):
+    g = golden("losses")
+    za, zb = T(g["za"]).cuda(), T(g["zb"]).cuda()
+    t = (0.2 * zb).clone().requires_grad_(True)
+    aab.vicreg_var_loss(t).backward()
+    assert rel_l2(t.grad, g["grad_var"]) < 1e-4
+    t = za.clone().requires_grad_(True)
+    aab.vicreg_cov_loss(t).backward()
+    assert rel_l2(t.grad, g["grad_cov"]) < 1e-4
+    a = za.clone().requires_grad_(True)
+    aab.mseloss(a, zb).backward()
+    assert rel_l2(a.grad, g["grad_mse_a"]) < 1e-5
+
+
+@pytest.mark.parametrize("b,c,t", [(2, 3, 5), (16, 64, 16), (33, 8, 40), (96, 64, 64)])
+def test_cov_and_var_vs_naive_oracle(aab, b, c, t):
+    "Gram-identity covariance loss == the reference's materialised (C T)^2 covariance (small T only)"
+    O = _oracle()
+    g = torch.Generator().manual_seed(b * 1000 + t)
+    mix = torch.randn(c * t, c * t, generator=g) / (c * t) ** 0.5
+    z = (torch.randn(b, c * t, generator=g) @ mix).reshape(b, c, t) + 0.3   # correlated features, non-zero mean
+    zd = z.double().requires_grad_(True)
+    lo = O.vicreg_cov_loss(zd)
+    lo.backward()
+    zc = z.cuda().requires_grad_(True)
+    lc = aab.vicreg_cov_loss(zc)
+    lc.backward()
+    assert abs(lc.item() - lo.item()) < 2e-4 * abs(lo.item())
+    assert rel_l2(zc.grad, zd.grad) < 2e-4
+    for l2 in (False, True):
+        zd2 = (0.5 * z).double().requires_grad_(True)
+        lo2 = O.vicreg_var_loss(zd2, l2_hinge=l2)
+        lo2.backward()
+        zc2 = (0.5 * z).cuda().requires_grad_(True)
+        lc2 = (aab.vicreg_var_loss_l2 if l2 else aab.vicreg_var_loss)(zc2)
+        lc2.backward()
+        assert abs(lc2.item() - lo2.item()) < 1e-5 * max(abs(lo2.item()), 1e-3)
+        assert rel_l2(zc2.grad, zd2.grad) < 1e-4
+
+
+def test_cov_loss_training_size_is_cheap_and_consistent(aab):
+    """[B,64,512] (the reference would build a 32768^2 = 4 GiB covariance): check the scalar against an
+    independent float64 Gram evaluation in torch and the gradient through a directional derivative."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    z = torch.randn(64, 64, 512, device="cuda", generator=g)
+    loss = aab.vicreg_cov_loss(z)
+    x = z.reshape(64, -1).double()
+    xc = x - x.mean(0, keepdim=True)
+    gram = xc @ xc.T
+    s = (xc * xc).sum(0)
+    ref = ((gram ** 2).sum() - (s ** 2).sum()) / (63 ** 2) / x.shape[1]
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
+    zc = z.clone().requires_grad_(True)
+    aab.vicreg_cov_loss(zc).backward()
+    d = torch.randn_like(z)
+    eps = 1e-2
+    fd = (aab.vicreg_cov_loss(z + eps * d).item() - aab.vicreg_cov_loss(z - eps * d).item()) / (2 * eps)
+    an = (zc.grad * d).sum().item()
+    assert abs(fd - an) < 2e-2 * max(abs(an), 1e-6)
+
+
+def test_latent_ops(aab):
+    O = _oracle()
+    from audio_algebra_b200 import latent_ops as L
+    g = torch.Generator().manual_seed(4)
+    z = torch.tanh(torch.randn(3, 64, 50, generator=g))
+    zc = z.cuda()
+    assert torch.equal(L.flip_channels(zc).cpu(), O.destructo_flip_channels(z))
+    assert torch.equal(L.flip_time(zc).cpu(), z.flip(dims=[2]))
+    assert rel_l2(L.sign_fold(zc), O.destructo_sign_fold(z.double())) < 1e-6
+    assert rel_l2(L.absmax_minus(zc), O.destructo_absmax_minus(z.double())) < 1e-6
+    assert rel_l2(L.tanh_drive(zc, 3.0), O.destructo_tanh_drive(z.double(), 3.0)) < 1e-5
+    wet, dry = torch.randn(5, 64, 50, generator=g), torch.randn(5, 64, 50, generator=g)
+    assert rel_l2(L.effect_transfer(zc, wet.cuda(), dry.cuda()), O.effect_transfer(z.double(), wet.double(), dry.double())) < 1e-6
+    zs = [torch.randn(2, 64, 33, generator=g) for _ in range(3)]
+    out = aab.latent_lincomb([t.cuda() for t in zs], [1.0, -1.0, 1.0])
+    assert rel_l2(out, zs[0].double() - zs[1].double() + zs[2].double()) < 1e-6
+    odd = [torch.randn(7, generator=g) for _ in range(2)]   # unaligned / tiny
+    assert rel_l2(aab.latent_lincomb([t.cuda()[1:] for t in odd], [2.0, 0.5]), 2 * odd[0][1:].double() + 0.5 * odd[1][1:].double()) < 1e-6
+
+
+class _ToyGiven(torch.nn.Module):
+    def __init__(self, w):
+        super().__init__()
+        self.register_buffer("w", w)
+
+    def encode(self, x):
+        return torch.tanh(torch.nn.functional.conv1d(x, self.w, stride=64))
+
+
+def test_do_mixing_mixer_golden(aab, golden):
+    g, gp = golden("mixing"), golden("projector")
+    aa = _load_aa(aab, gp)
+    toy = _ToyGiven(T(g["toy_w"])).cuda()
+    stems = [T(g["stem0"]).cuda(), T(g["stem1"]).cuda()]
+    zsum, zmix, arch = aab.do_mixing(stems, T(g["faders"]).cuda(), toy, aa, "cuda")
+    assert rel_l2(zsum, g["zsum"]) < 1e-4 and rel_l2(zmix, g["zmix"]) < 1e-4
+    assert rel_l2(arch["ymix"], g["ymix"]) < 1e-4 and rel_l2(arch["ymix_recon"], g["ymix_recon"]) < 1e-4
+    assert rel_l2(arch["mix"], g["mix"]) < 1e-6 and rel_l2(arch["ysum"], g["ysum"]) < 1e-4
+    for i in range(2):
+        assert rel_l2(arch["zs"][i], g[f"zs{i}"]) < 1e-4 and rel_l2(arch["yrecons"][i], g[f"yrecons{i}"]) < 1e-4
+    # loss terms exactly as train_aa_mixer_accel.py:504-517
+    y = toy.encode(stems[0])
+    z, yrecon = aa(y)
+    L_mix = aab.mseloss(zsum, zmix)
+    L_var = (aab.vicreg_var_loss(zsum) + aab.vicreg_var_loss(zmix)) / 2
+    L_cov = (aab.vicreg_cov_loss(zsum) + aab.vicreg_cov_loss(zmix)) / 2
+    L_rec = aab.mseloss(y, yrecon) + aab.mseloss(arch["ymix"], arch["ymix_recon"])
+    for v, k in [(L_mix, "L_mix"), (L_var, "L_var"), (L_cov, "L_cov"), (L_rec, "L_rec")]:
+        assert abs(v.item() - g[k]) < 2e-4 * max(abs(g[k]), 1e-3), k
+    (L_mix + L_var + L_cov + L_rec).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in aa.parameters())
+
+
+def test_do_mixing_effects_golden(aab, golden):
+    g, gp = golden("mixing"), golden("projector")
+    aa = _load_aa(aab, gp)
+    toy = _ToyGiven(T(g["toy_w"])).cuda()
+    batch = {k: T(g["fx_" + k]) for k in ("a1", "b1", "a2", "b2")}
+    arch = aab.aa_effects.do_mixing(batch, toy, aa, "cuda")
+    for i in range(4):
+        assert rel_l2(arch["ys"][i], g[f"fx_ys{i}"]) < 1e-4
+        assert rel_l2(arch["zs"][i], g[f"fx_zs{i}"]) < 1e-4
+        assert rel_l2(arch["yrecons"][i], g[f"fx_yrecons{i}"]) < 1e-4
+    O = _oracle()
+    L = aab.aa_effects.effects_losses(arch)
+    Lo = O.effects_losses([T(g[f"fx_zs{i}"]).double() for i in range(4)], [T(g[f"fx_ys{i}"]).double() for i in range(4)],
+                          [T(g[f"fx_yrecons{i}"]).double() for i in range(4)])
+    for k in ("mix_loss", "var_loss", "cov_loss", "aa_recon_loss", "loss"):
+        assert abs(L[k].item() - Lo[k].item()) < 3e-4 * max(abs(Lo[k].item()), 1e-3), k
+    L["loss"].backward()
+
+
+def test_get_stems_faders_recipe(aab, golden):
+    import random
+    g = golden("mixing")
+    random.seed(0)
+    torch.manual_seed(0)
+    b0, b1 = T(g["stem0"]).cuda(), T(g["stem1"])
+    stems, faders, it = aab.get_stems_faders(b0, iter([b1]), [b1], maxstems=2)
+    assert len(stems) == 2 and stems[1].is_cuda and faders.is_cuda
+    assert np.allclose(faders.cpu().numpy(), g["faders_seed0"], atol=1e-6)
+
+
+def test_pca_accumulation_golden(aab, golden):
+    g = golden("pca")
+    rc = aab.pca.RunningCovariance(64, "cuda")
+    for bi in range(2):
+        rc.update(T(g[f"ys{bi}"]).cuda())
+    assert int(rc.count.item()) == int(g["npoints"][0])
+    assert rel_l2(rc.cov_numerator, g["cov_numerator"]) < 1e-4
+    assert rel_l2(rc.eigenvalues(), g["lambdas"]) < 1e-3
+    # ragged: C not a multiple of 64, T not a multiple of the tile
+    O = _oracle()
+    y = torch.tanh(torch.randn(3, 10, 45, generator=torch.Generator().manual_seed(1)))
+    rc2 = aab.pca.RunningCovariance(10, "cuda").update(y.cuda())
+    num, n = O.pca_cov_numerator(y.double())
+    assert rel_l2(rc2.cov_numerator, num) < 1e-5 and int(rc2.count.item()) == n
+
+
+def test_adam_matches_torch(aab):
+    from audio_algebra_b200.training import FlatAdam
+    O = _oracle()
+    torch.manual_seed(0)
+    p0 = torch.randn(33280)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=5e-4)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-3, total_steps=50)
+    mine = FlatAdam(p0.clone().cuda(), lr=5e-4, max_lr=1e-3, total_steps=50)
+    for step in range(20):
+        gr = torch.randn(33280)
+        pt.grad = gr.clone()
+        opt.step(); sched.step()
+        mine.step(gr.cuda())
+    assert rel_l2(mine.params, pt.detach()) < 1e-6
