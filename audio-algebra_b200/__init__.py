@@ -11,4 +11,4 @@ from .given_models import (GivenModelClass, SpectrogramAE, MagSpectrogramAE, Mag
                            MelSpectrogramAE)
 from .aa_mixer import (EmbedBlock, AudioAlgebra, get_stems_faders, do_mixing, mseloss, vicreg_var_loss,  # noqa: F401
                        vicreg_var_loss_l2, vicreg_cov_loss, off_diagonal, latent_lincomb)
-from . import aa_mixer, aa_effects, latent_ops, pca, given_models  # noqa: F401
+from . import aa_mixer, aa_effects, latent_ops, pca, given_models, parallel, training  # noqa: F401

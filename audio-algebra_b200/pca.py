@@ -8,6 +8,7 @@ import torch
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 from .aa_mixer import _f32c, _ws
+from .parallel import allreduce_sum_
 
 __all__ = ['sorted_eig', 'RunningCovariance']
 
@@ -42,10 +43,8 @@ class RunningCovariance:
         return self
 
     def all_reduce(self, group=None):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.cov_numerator, group=group)
-            dist.all_reduce(self.count, group=group)
+        allreduce_sum_(self.cov_numerator, group)
+        allreduce_sum_(self.count, group)
         return self
 
     def covariance(self):

@@ -8,6 +8,7 @@ import math
 import torch
 
 from ._lib import lib, check, ptr, stream_ptr
+from .parallel import allreduce_mean_
 from .aa_mixer import (AudioAlgebra, do_mixing, get_stems_faders, mseloss, vicreg_var_loss, vicreg_cov_loss)  # noqa: F401
 
 __all__ = ['FlatAdam', 'onecycle_lr', 'onecycle_beta1', 'mixer_losses', 'MixerTrainer']
@@ -88,21 +89,14 @@ class MixerTrainer:
     def step(self, stems, faders, batch=None):
         """stems: list of [B,2,N] device tensors (stems[0] doubles as `batch` of the reference loop);
         returns the dict of (detached, on-device) loss terms -- no host sync."""
-        import torch.distributed as dist
         self.flat_grad.zero_()
         device = stems[0].device
         zsum, zmix, archive = do_mixing(stems, faders, self.given_model, self.aa_model, device)
-        with torch.no_grad():
-            y = archive['ys'][0] if batch is None else self.given_model.encode(batch)
-        # the reference re-encodes `batch` un-faded; with batch given we follow it exactly
-        if batch is None:
-            with torch.no_grad():
-                y = self.given_model.encode(stems[0])
+        with torch.no_grad():   # the reference re-encodes the un-faded batch (= stems[0]) for the recon term
+            y = self.given_model.encode(stems[0] if batch is None else batch)
         z, yrecon = self.aa_model(y)
         losses = mixer_losses(zsum, zmix, y, yrecon, archive['ymix'], archive['ymix_recon'])
         losses['loss'].backward()
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad, group=self.group)
-            self.flat_grad.div_(self.world)
+        allreduce_mean_(self.flat_grad, self.group)
         self.opt.step(self.flat_grad)
         return {k: v.detach() for k, v in losses.items()}
