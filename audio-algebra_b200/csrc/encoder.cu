@@ -1,0 +1,275 @@
+// Given-model conv encoder ("f: audio -> y"): the restated SoundStreamXLEncoder of the reference's
+// DiffusionDVAE (aa_mixer.py:118-131 constructor arguments; architecture per SURVEY.md Appendix A --
+// third-party source, PARITY UNPINNED upstream):
+//   Conv1d(in->cap,k7,p3) ELU  [ResUnit(d=1) ELU ResUnit(3) ELU ResUnit(9) ELU Conv1d(k=2s,stride s,pad ceil(s/2)) ELU] x5
+//   Conv1d(c_last->latent,k3,p1)  [tanh for encode_it / DVAEWrapper.encode, none for DiffusionDVAE.encode]
+//   ResUnit(x) = x + Conv1d(k1)(ELU(Conv1d(k7, dilation d, padding 3d)(x)))
+// The layer list is data (a table of {cin, cout, k, stride, dilation, pad, residual role}) so a corrected
+// upstream architecture is a table change.  Every conv is one kernel with a fused epilogue:
+//   bias (+ residual) -> ELU (-> tanh on the last layer); the first layer also fuses the fader-scaled sum
+//   of stems (aa_mixer.py:303,309: fadedstem = s*f; mix += fadedstem) into its load.
+// This file: layer table, weight storage, sequencing, and the fp32 CUDA-core conv kernel (exact-parity
+// path).  The bf16 tensor-core path (tcgen05 implicit GEMM) lives in conv_tc.cu.
+#include "aa_common.cuh"
+#include "encoder.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace {
+
+constexpr int CT = 64;    // output-channel tile
+constexpr int LT = 64;    // output-position tile
+constexpr int CK = 8;     // input channels per smem chunk
+constexpr int XW = 272;   // max input strip width: 63*stride + (k-1)*dil + 1 <= 63*4 + 7 + 1 = 260; 63 + 6*9 + 1 = 118
+
+struct ConvArgs {
+  const float* x[4];      // up to 4 stems (layer 0) or one activation tensor
+  float fader[4];
+  int n_in;
+  const float* w;         // [cout][cin][k]
+  const float* bias;      // [cout]
+  const float* res;       // residual [B][cout][lout] or NULL
+  float* out;             // [B][cout][lout]
+  int cin, cout, lin, lout, k, stride, dil, pad;
+  int elu, tanh_out;
+};
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+
+__global__ void __launch_bounds__(256) conv1d_f32_kernel(const ConvArgs a) {
+  __shared__ float Xs[CK][XW];
+  __shared__ float Ws[CK][8][CT + 1];   // [ci][k][co]
+  const int b = blockIdx.z;
+  const int co0 = blockIdx.y * CT, l0 = blockIdx.x * LT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: positions, ty: channels
+  const int span = (LT - 1) * a.stride + (a.k - 1) * a.dil + 1;
+  const int in0 = l0 * a.stride - a.pad;
+  float acc[4][4] = {};
+  for (int c0 = 0; c0 < a.cin; c0 += CK) {
+    for (int e = threadIdx.x; e < CK * span; e += 256) {
+      const int ci = e / span, j = e % span;
+      const int c = c0 + ci, pos = in0 + j;
+      float v = 0.f;
+      if (c < a.cin && pos >= 0 && pos < a.lin) {
+        const long long off = ((long long)b * a.cin + c) * a.lin + pos;
+        v = a.fader[0] * a.x[0][off];
+        for (int s = 1; s < a.n_in; ++s) v = fmaf(a.fader[s], a.x[s][off], v);
+      }
+      Xs[ci][j] = v;
+    }
+    for (int e = threadIdx.x; e < CK * a.k * CT; e += 256) {
+      const int co = e % CT, r = e / CT, kk = r % a.k, ci = r / a.k;
+      const int c = c0 + ci, o = co0 + co;
+      Ws[ci][kk][co] = (c < a.cin && o < a.cout) ? a.w[((long long)o * a.cin + c) * a.k + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ci = 0; ci < CK; ++ci) {
+      for (int kk = 0; kk < a.k; ++kk) {
+        float wv[4], xv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          wv[e] = Ws[ci][kk][ty * 4 + e];
+          xv[e] = Xs[ci][(tx * 4 + e) * a.stride + kk * a.dil];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = co0 + ty * 4 + i;
+    if (o >= a.cout) continue;
+    const float bv = a.bias[o];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = l0 + tx * 4 + j;
+      if (l >= a.lout) continue;
+      const long long off = ((long long)b * a.cout + o) * a.lout + l;
+      float v = acc[i][j] + bv;
+      if (a.res) v += a.res[off];
+      if (a.elu) v = elu1(v);
+      if (a.tanh_out) v = tanhf(v);
+      a.out[off] = v;
+    }
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+int aa::build_layer_table(const AaEncoderCfg& cfg, std::vector<aa::ConvLayer>& L) {
+  L.clear();
+  AA_REQUIRE(cfg.n_blocks >= 1 && cfg.n_blocks <= 8, "n_blocks=%d", cfg.n_blocks);
+  AA_REQUIRE(cfg.in_channels >= 1 && cfg.capacity >= 1 && cfg.latent_dim >= 1, "bad encoder config");
+  auto push = [&](int cin, int cout, int k, int stride, int dil, int pad, int elu, int role) {
+    aa::ConvLayer l{};
+    l.cin = cin; l.cout = cout; l.k = k; l.stride = stride; l.dil = dil; l.pad = pad; l.elu = elu; l.role = role;
+    L.push_back(l);
+  };
+  int c = cfg.capacity;
+  push(cfg.in_channels, c, 7, 1, 1, 3, 1, aa::ROLE_PLAIN);
+  for (int i = 0; i < cfg.n_blocks; ++i) {
+    const int cin = c, cout = cfg.c_mults[i] * cfg.capacity, s = cfg.strides[i];
+    AA_REQUIRE(s >= 1 && s <= 4, "stride %d not supported (1..4)", s);
+    const int dils[3] = {1, 3, 9};
+    for (int d : dils) {
+      push(cin, cin, 7, 1, d, 3 * d, 1, aa::ROLE_RES_FIRST);   // h = ELU(conv_k7(x))
+      push(cin, cin, 1, 1, 1, 0, 1, aa::ROLE_RES_SECOND);      // y = ELU(conv_k1(h) + x)
+    }
+    push(cin, cout, 2 * s, s, 1, (s + 1) / 2, 1, aa::ROLE_PLAIN);
+    c = cout;
+  }
+  push(c, cfg.latent_dim, 3, 1, 1, 1, 0, aa::ROLE_PLAIN);
+  return AA_OK;
+}
+
+struct AaEncoder {
+  AaEncoderCfg cfg;
+  std::vector<aa::ConvLayer> layers;
+  std::vector<float*> w, b;          // device fp32 copies, [cout][cin][k] / [cout]
+  aa::TcState* tc = nullptr;         // bf16 tensor-core path state (conv_tc.cu), created lazily
+  int total_stride = 1;
+};
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int aa_encoder_create(const AaEncoderCfg* cfg, AaEncoder** out) {
+  AA_REQUIRE(cfg && out, "NULL argument");
+  int rc = aa_check_device();
+  if (rc != AA_OK) return rc;
+  AaEncoder* e = new AaEncoder();
+  e->cfg = *cfg;
+  rc = aa::build_layer_table(*cfg, e->layers);
+  if (rc != AA_OK) { delete e; return rc; }
+  e->w.assign(e->layers.size(), nullptr);
+  e->b.assign(e->layers.size(), nullptr);
+  for (int i = 0; i < cfg->n_blocks; ++i) e->total_stride *= cfg->strides[i];
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    const auto& l = e->layers[i];
+    AA_CUDA(cudaMalloc(&e->w[i], sizeof(float) * (size_t)l.cout * l.cin * l.k));
+    AA_CUDA(cudaMalloc(&e->b[i], sizeof(float) * l.cout));
+    AA_CUDA(cudaMemset(e->w[i], 0, sizeof(float) * (size_t)l.cout * l.cin * l.k));
+    AA_CUDA(cudaMemset(e->b[i], 0, sizeof(float) * l.cout));
+  }
+  *out = e;
+  return AA_OK;
+}
+
+int aa_encoder_destroy(AaEncoder* e) {
+  if (!e) return AA_OK;
+  for (auto p : e->w) cudaFree(p);
+  for (auto p : e->b) cudaFree(p);
+  aa::tc_destroy(e->tc);
+  delete e;
+  return AA_OK;
+}
+
+int aa_encoder_num_layers(const AaEncoder* e) { return e ? (int)e->layers.size() : 0; }
+
+int aa_encoder_layer_shape(const AaEncoder* e, int layer, int* cout, int* cin, int* k) {
+  AA_REQUIRE(e && layer >= 0 && layer < (int)e->layers.size(), "bad layer index %d", layer);
+  if (cout) *cout = e->layers[layer].cout;
+  if (cin) *cin = e->layers[layer].cin;
+  if (k) *k = e->layers[layer].k;
+  return AA_OK;
+}
+
+int aa_encoder_set_weights(AaEncoder* e, int layer, const float* w_dev, const float* b_dev, void* stream) {
+  AA_REQUIRE(e && layer >= 0 && layer < (int)e->layers.size(), "bad layer index %d", layer);
+  AA_REQUIRE(w_dev && b_dev, "NULL weights");
+  const auto& l = e->layers[layer];
+  AA_CUDA(cudaMemcpyAsync(e->w[layer], w_dev, sizeof(float) * (size_t)l.cout * l.cin * l.k, cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  AA_CUDA(cudaMemcpyAsync(e->b[layer], b_dev, sizeof(float) * l.cout, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (e->tc) aa::tc_invalidate_weights(e->tc);
+  return AA_OK;
+}
+
+static int64_t max_act_elems(const AaEncoder* e, int64_t batch, int64_t n) {
+  int64_t l = n, mx = 0;
+  for (const auto& ly : e->layers) {
+    const int64_t lout = (l + 2 * ly.pad - (int64_t)ly.dil * (ly.k - 1) - 1) / ly.stride + 1;
+    mx = std::max(mx, batch * ly.cout * lout);
+    l = lout;
+  }
+  return mx;
+}
+
+int aa_encoder_out_length(const AaEncoder* e, int64_t n, int64_t* t_out) {
+  AA_REQUIRE(e && t_out, "NULL argument");
+  int64_t l = n;
+  for (const auto& ly : e->layers) l = (l + 2 * ly.pad - (int64_t)ly.dil * (ly.k - 1) - 1) / ly.stride + 1;
+  *t_out = l;
+  return AA_OK;
+}
+
+int64_t aa_encoder_workspace_bytes(const AaEncoder* e, int64_t batch, int64_t n, int dtype) {
+  if (!e) return 0;
+  const int64_t elems = max_act_elems(e, batch, n);
+  if (dtype == AA_DTYPE_BF16) return aa::tc_workspace_bytes(e->layers, batch, n);
+  return 3 * elems * (int64_t)sizeof(float) + 256;
+}
+
+int aa_encoder_forward(AaEncoder* e, const float* const* stems_host, const float* faders_host, int n_stems, int64_t batch,
+                       int64_t n, int apply_tanh, int dtype, float* y, void* workspace, void* stream) {
+  AA_REQUIRE(e && stems_host && y && workspace, "NULL argument");
+  AA_REQUIRE(n_stems >= 1 && n_stems <= 4, "n_stems=%d must be in [1,4]", n_stems);
+  AA_REQUIRE(batch >= 0 && n >= 1, "bad shape");
+  if (batch == 0) return AA_OK;
+  for (int s = 0; s < n_stems; ++s) AA_REQUIRE(stems_host[s] != nullptr, "stem %d is NULL", s);
+  if (dtype == AA_DTYPE_BF16) {
+    if (!e->tc) {
+      int rc = aa::tc_create(&e->tc, e->layers);
+      if (rc != AA_OK) return rc;
+    }
+    return aa::tc_forward(e->tc, e->layers, e->w, e->b, stems_host, faders_host, n_stems, batch, n, apply_tanh, y, workspace,
+                          (cudaStream_t)stream);
+  }
+  AA_REQUIRE(dtype == AA_DTYPE_F32, "unknown dtype %d", dtype);
+  AA_REQUIRE(batch <= 65535, "fp32 path: batch <= 65535 per call");
+  const int64_t elems = max_act_elems(e, batch, n);
+  float* buf[3] = {reinterpret_cast<float*>(workspace), reinterpret_cast<float*>(workspace) + elems,
+                   reinterpret_cast<float*>(workspace) + 2 * elems};
+  int cur = -1;            // buffer holding the current activation (-1: the input stems)
+  int res_buf = -1;        // buffer holding the residual-unit input
+  int64_t l = n;
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    const auto& ly = e->layers[i];
+    const int64_t lout = (l + 2 * ly.pad - (int64_t)ly.dil * (ly.k - 1) - 1) / ly.stride + 1;
+    AA_REQUIRE(lout >= 1 && l < (1LL << 31), "input too short / too long for layer %zu", i);
+    ConvArgs a{};
+    if (cur < 0) {
+      a.n_in = n_stems;
+      for (int s = 0; s < n_stems; ++s) { a.x[s] = stems_host[s]; a.fader[s] = faders_host ? faders_host[s] : 1.0f; }
+    } else {
+      a.n_in = 1; a.x[0] = buf[cur]; a.fader[0] = 1.0f;
+    }
+    const bool last = (i + 1 == e->layers.size());
+    int dst = 0;
+    while (dst == cur || dst == res_buf) ++dst;
+    if (ly.role == aa::ROLE_RES_FIRST) res_buf = cur;          // keep x of the residual unit
+    a.w = e->w[i]; a.bias = e->b[i];
+    a.res = (ly.role == aa::ROLE_RES_SECOND) ? buf[res_buf] : nullptr;
+    a.out = last ? y : buf[dst];
+    a.cin = ly.cin; a.cout = ly.cout; a.lin = (int)l; a.lout = (int)lout; a.k = ly.k; a.stride = ly.stride; a.dil = ly.dil;
+    a.pad = ly.pad; a.elu = ly.elu; a.tanh_out = (last && apply_tanh) ? 1 : 0;
+    dim3 grid((unsigned)((lout + LT - 1) / LT), (unsigned)((ly.cout + CT - 1) / CT), (unsigned)batch);
+    conv1d_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    AA_LAUNCH_CHECK();
+    if (ly.role == aa::ROLE_RES_SECOND) res_buf = -1;
+    cur = dst;
+    l = lout;
+  }
+  return AA_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -16,7 +16,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 
-__all__ = ['GivenModelClass', 'SpectrogramAE', 'MagSpectrogramAE', 'MagDPhaseSpectrogramAE', 'MelSpectrogramAE']
+__all__ = ['GivenModelClass', 'SpectrogramAE', 'MagSpectrogramAE', 'MagDPhaseSpectrogramAE', 'MelSpectrogramAE', 'DVAEWrapper']
 
 
 class GivenModelClass(nn.Module):
@@ -209,10 +209,12 @@ class _StftFrontEnd(GivenModelClass):
                                                           self.fb)
         return self._plans[device_index]
 
-    def _run(self, waveform, mode):
+    def _run(self, waveform, mode, out=None):
         """waveform [..., N] float32 -> [..., F|n_mels, T].  CUDA input: stream-ordered kernel on the
         current stream.  CPU input: H2D, kernel, D2H (result returned on the CPU, like the reference
-        keeps the input's device) -- the mel variant pipelines the copies in chunks."""
+        keeps the input's device) -- the mel variant pipelines the copies in chunks; `out` may be a
+        preallocated (ideally pinned) CPU tensor, as in the reference's bulk-encode loop
+        (xae_dataset.ipynb cell 50 writes into a preallocated `reps` array)."""
         self.orig_shape = waveform.shape
         if waveform.dtype != torch.float32:
             waveform = waveform.float()
@@ -226,7 +228,11 @@ class _StftFrontEnd(GivenModelClass):
         with torch.cuda.device(dev):
             if on_cpu and mode == "mel":
                 x = waveform.contiguous()
-                out = torch.empty((*lead, bins, n_frames), dtype=torch.float32, pin_memory=True)
+                shape = (*lead, bins, n_frames)
+                if out is None:
+                    out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+                elif tuple(out.shape) != shape or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+                    raise ValueError(f"out must be a contiguous float32 CPU tensor of shape {shape}")
                 check(lib.aa_stft_mel_f32_host(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), 64))
                 return out
             x = waveform.to(f"cuda:{dev}", non_blocking=True).contiguous()
@@ -295,4 +301,54 @@ class MelSpectrogramAE(_StftFrontEnd):
         self.sample_rate = sample_rate
 
     def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
-        return self._run(waveform, "mel")
+        return self._run(waveform, "mel", out=kwargs.get("out"))
+
+
+class DVAEWrapper(GivenModelClass):
+    """Wrapper for DiffusionDVAE (given_models.py:286-358): encode() = tanh(encoder_ema(waveform)).
+    The reference also draws decoder noise of the input's size on every encode (given_models.py:320);
+    it is only consumed by decode(), which is out of scope, so it is not generated."""
+
+    def __init__(self,
+                 args_dict={'num_quantizers': 0, 'sample_size': 65536, 'demo_steps': 50, 'sample_rate': 48000, 'latent_dim': 64,
+                            'pqmf_bands': 1, 'ema_decay': 0.995},
+                 debug=True, **kwargs):
+        super().__init__()
+        from .DiffusionDVAE import DiffusionDVAE
+
+        class DictObj:
+            def __init__(self, in_dict: dict):
+                for key, val in in_dict.items():
+                    if isinstance(val, (list, tuple)):
+                        setattr(self, key, [DictObj(x) if isinstance(x, dict) else x for x in val])
+                    else:
+                        setattr(self, key, DictObj(val) if isinstance(val, dict) else val)
+
+        self.global_args = DictObj(dict(args_dict, **{k: v for k, v in kwargs.items() if k == "compute_dtype"}))
+        self.model = DiffusionDVAE(self.global_args)
+        self.model.eval()
+        self.noise = None
+        self.demo_steps = self.global_args.demo_steps
+        self.demo_samples = self.global_args.sample_size
+        self.debug = debug
+        self.ckpt_info = {'ckpt_url': 'https://drive.google.com/file/d/1C3NMdQlmOcArGt1KL7pH32KtXVCOfXKr/view?usp=sharing',
+                          'ckpt_hash': '6a304c3e89ea3f7ca023f4c9accc5df8de0504595db41961cc7e8b0d07876ef5',
+                          'gdrive_path': 'MyDrive/AI/checkpoints/DiffusionDVAE.ckpt',
+                          'ckpt_path': '~/checkpoints/dvae_checkpoint.ckpt'}
+
+    def setup(self, gdrive=True):
+        """The reference downloads the 4 GB Lightning checkpoint here (given_models.py:340-356) and keeps
+        random weights when that fails; there is no network in this build, so weights stay as initialised
+        (or as loaded through load_state_dict / model.load_oracle_weights)."""
+        if self.debug:
+            print("DVAEWrapper.setup: no checkpoint download in this build; keeping current encoder weights")
+
+    def encode_it(self, demo_reals):
+        return self.model.encode_it(demo_reals), None
+
+    def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
+        self.orig_shape = waveform.shape
+        self.demo_samples = waveform.shape[-1]
+        on_cpu = not waveform.is_cuda
+        reps = self.model.encode_it(waveform)
+        return reps.cpu() if on_cpu else reps

@@ -138,6 +138,38 @@ int aa_vicreg_cov_bwd_f32(const float* z, const float* stats, const float* gram,
                           const float* gloss, float gscale, float* grad_z, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Given-model conv encoder: SoundStreamXLEncoder as constructed by DiffusionDVAE.__init__
+ * (aa_mixer.py:118-131) and called by DiffusionDVAE.encode (:165-168, no tanh) / encode_it (:175-195,
+ * tanh) / DVAEWrapper.encode (given_models.py:313-338).  The architecture is restated from the
+ * third-party `audio-diffusion` package (parity unpinned upstream).
+ * Weights: nn.Conv1d layout [cout][cin][k] f32 + bias [cout], layer order = the order
+ * aa_encoder_layer_shape enumerates (conv_in; per block: 3 x (res conv k7, res conv k1), down conv; conv_out).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct AaEncoder AaEncoder;
+typedef struct AaEncoderCfg {
+  int in_channels;  /* 2 * pqmf_bands                       */
+  int capacity;     /* 32                                   */
+  int latent_dim;   /* 64                                   */
+  int n_blocks;     /* 5                                    */
+  int c_mults[8];   /* {2,4,8,16,32}                        */
+  int strides[8];   /* {4,4,2,2,2}                          */
+} AaEncoderCfg;
+int aa_encoder_create(const AaEncoderCfg* cfg, AaEncoder** enc);
+int aa_encoder_destroy(AaEncoder* enc);
+int aa_encoder_num_layers(const AaEncoder* enc);
+int aa_encoder_layer_shape(const AaEncoder* enc, int layer, int* cout, int* cin, int* k);
+/* copies device tensors into the handle (and invalidates packed bf16 copies) */
+int aa_encoder_set_weights(AaEncoder* enc, int layer, const float* w_dev, const float* b_dev, void* stream);
+int aa_encoder_out_length(const AaEncoder* enc, int64_t n, int64_t* t_out);
+int64_t aa_encoder_workspace_bytes(const AaEncoder* enc, int64_t batch, int64_t n, int dtype);
+/* y [B][latent][T'] f32 = encoder(sum_j faders_host[j] * stems[j]) (tanh applied iff apply_tanh).
+ * stems_host: host array of n_stems (1..4) device pointers to [B][in_channels][n] f32 tensors; the
+ * fader-scaled sum (aa_mixer.py:303,309) is fused into the first layer's load.  dtype selects the
+ * arithmetic: AA_DTYPE_F32 (CUDA-core fp32, exact-parity path) or AA_DTYPE_BF16 (tcgen05, fp32 accumulate). */
+int aa_encoder_forward(AaEncoder* enc, const float* const* stems_host, const float* faders_host, int n_stems,
+                       int64_t batch, int64_t n, int apply_tanh, int dtype, float* y, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Projector (aa_mixer.py:205-267): one half (encode or decode) of AudioAlgebra =
  *   4 EmbedBlocks (Linear + exact-erf GELU on the first three, inner residual iff in==out) applied to
  *   x^T, transposed back, plus the outer residual -- fused in one kernel on the channel-major tensor.

@@ -1,0 +1,110 @@
+"""GPU parity of the conv encoder (DiffusionDVAE.encode / encode_it, DVAEWrapper.encode) against the
+oracle restatement with shared seeded random-init weights.  NOTE: the oracle itself is a restatement of a
+third-party module whose source is not in the reference tree (PARITY UNPINNED upstream);
+the reference pins only the shape [6,2,65536] -> [6,64,512] (Destructo.ipynb cell 17).
+Tolerances (BASELINE.json): fp32 relative L2 <= 1e-3 on embeddings; bf16 cosine >= 0.999 per embedding."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import audio_algebra_b200 as aab
+    from oracle import aa_oracle as O
+    torch.manual_seed(0)
+    enc_o = O.SoundStreamXLEncoderOracle().eval()
+    dv = aab.DVAEWrapper(debug=False)
+    dv.model.load_oracle_weights(enc_o)
+    return aab, O, enc_o, dv.cuda()
+
+
+def _x(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(*shape, generator=g) - 0.5
+
+
+def test_destructo_shape_kat(setup):
+    aab, O, enc_o, dv = setup
+    y = dv.encode(torch.zeros(6, 2, 65536, device="cuda"))
+    assert tuple(y.shape) == (6, 64, 512) and y.dtype == torch.float32   # Destructo.ipynb cell 17
+
+
+def test_fp32_encode_it_and_encode(setup):
+    aab, O, enc_o, dv = setup
+    x = _x((2, 2, 16384), 1)
+    y = dv.encode(x.cuda())                              # tanh(encoder_ema(x))
+    assert rel_l2(y, O.dvae_encode_it(enc_o, x)) < 1e-3
+    dv.model.eval()
+    y2 = dv.model.encode(x.cuda())                       # no tanh
+    assert rel_l2(y2, O.dvae_encode(enc_o, x)) < 1e-3
+    assert rel_l2(torch.tanh(y2), y) < 1e-6
+    assert dv.encode(x).device.type == "cpu"             # CPU in -> CPU out
+
+
+def test_fp32_ragged_lengths_and_batch(setup):
+    aab, O, enc_o, dv = setup
+    for shape, seed in [((1, 2, 128), 2), ((3, 2, 5000), 3), ((1, 2, 131072), 4)]:
+        x = _x(shape, seed)
+        ref = O.dvae_encode_it(enc_o, x)
+        y = dv.encode(x.cuda())
+        assert tuple(y.shape) == tuple(ref.shape)
+        assert rel_l2(y, ref) < 1e-3
+    assert tuple(dv.encode(torch.zeros(0, 2, 4096, device="cuda")).shape) == (0, 64, 32)
+
+
+def test_fused_fader_mix(setup):
+    "encode(sum f_i s_i) with the scale-and-sum folded into the first conv's load (aa_mixer.py:303,309)"
+    aab, O, enc_o, dv = setup
+    s0, s1 = _x((2, 2, 8192), 5), _x((2, 2, 8192), 6)
+    f = [1.4630, -0.5718]
+    y = dv.model.encode_mix([s0.cuda(), s1.cuda()], f)
+    assert rel_l2(y, O.dvae_encode(enc_o, f[0] * s0 + f[1] * s1)) < 1e-3
+
+
+def test_config1_destructo_chain(setup):
+    "BASELINE config 1: one 2^17 stereo chunk -> encoder -> tanh -> latent add/subtract + Destructo ops"
+    aab, O, enc_o, dv = setup
+    from audio_algebra_b200 import latent_ops as L
+    x, wet, dry = _x((1, 2, 131072), 7), _x((1, 2, 131072), 8), _x((1, 2, 131072), 9)
+    z, zw, zd = [dv.encode(t.cuda()) for t in (x, wet, dry)]
+    zo, zwo, zdo = [O.dvae_encode_it(enc_o, t).double() for t in (x, wet, dry)]
+    assert tuple(z.shape) == (1, 64, 1024)
+    assert rel_l2(L.effect_transfer(z, zw, zd), O.effect_transfer(zo, zwo, zdo)) < 1e-3
+    assert rel_l2(L.sign_fold(L.flip_channels(z)), O.destructo_sign_fold(O.destructo_flip_channels(zo))) < 1e-3
+
+
+def test_weight_update_is_picked_up(setup):
+    aab, O, enc_o, dv = setup
+    import copy
+    x = _x((1, 2, 4096), 10)
+    y0 = dv.encode(x.cuda())
+    dv2 = copy.deepcopy(dv)
+    with torch.no_grad():
+        dv2.model.encoder_ema.conv_out.bias.add_(0.25)
+    y1 = dv2.encode(x.cuda())
+    assert rel_l2(torch.atanh(y1.clamp(-0.999, 0.999)) - 0.25, torch.atanh(y0.clamp(-0.999, 0.999))) < 1e-3
+    assert rel_l2(dv.encode(x.cuda()), y0) < 1e-7
+
+
+def test_bf16_mode_cosine(setup):
+    aab, O, enc_o, dv = setup
+    dvb = aab.DVAEWrapper(debug=False, compute_dtype="bf16")
+    dvb.model.load_oracle_weights(enc_o)
+    dvb = dvb.cuda()
+    for shape, seed in [((2, 2, 16384), 11), ((3, 2, 5000), 12), ((1, 2, 131072), 13)]:
+        x = _x(shape, seed)
+        y = dvb.encode(x.cuda()).cpu().double()
+        ref = O.dvae_encode_it(enc_o, x).double()
+        assert tuple(y.shape) == tuple(ref.shape)
+        cos = torch.nn.functional.cosine_similarity(y.flatten(1), ref.flatten(1), dim=1)
+        assert cos.min().item() >= 0.999, cos
+    s0, s1 = _x((2, 2, 8192), 5), _x((2, 2, 8192), 6)
+    f = [1.4630, -0.5718]
+    y = dvb.model.encode_mix([s0.cuda(), s1.cuda()], f).cpu().double()
+    ref = O.dvae_encode(enc_o, f[0] * s0 + f[1] * s1).double()
+    cos = torch.nn.functional.cosine_similarity(y.flatten(1), ref.flatten(1), dim=1)
+    assert cos.min().item() >= 0.999, cos
