@@ -1,16 +1,575 @@
-// bf16 tensor-core path of the encoder (tcgen05 implicit-GEMM Conv1d).  Placeholder until the kernel lands.
+// bf16 tensor-core path of the conv encoder: Conv1d as an implicit GEMM on tcgen05 (sm_100a).
+//
+// Activations are kept channels-last in bf16 ([B][L][C], C contiguous) between layers, so that
+//   * an input tile for filter tap j is ONE 3-D TMA box (channels x 128 positions x 1 batch element) whose row
+//     coordinate is simply shifted by the tap offset; conv zero padding = TMA out-of-bounds zero fill;
+//   * strided down-convs (k = 2s, stride s, pad s/2) become a 3-tap stride-1 conv on the view
+//     [B][L/s][s*C] (row offsets -1, 0, +1 with partial column ranges), i.e. the same kernel;
+//   * both MMA operands are K-major: A = activations [128 rows x BK channels], B = weights
+//     [BN out-channels x BK] repacked once as W2[cout][tap-major K] bf16.
+// One persistent CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer
+// (accumulators in TMEM, double buffered), warps 2..5 = epilogue (tcgen05.ld -> bias (+ residual) -> ELU
+// -> bf16 channels-last store, or fp32 channel-major (+ tanh) for the last layer).
+// The first layer (2 input channels, K = 14) has no tensor-core shape and is memory bound: a CUDA-core
+// kernel fuses the fader-scaled stem sum, the conv, ELU and the fp32 [B][2][N] -> bf16 [B][N][32] layout change.
 #include "aa_common.cuh"
 #include "encoder.cuh"
 
-namespace aa {
-struct TcState { int dummy; };
-int tc_create(TcState** st, const std::vector<ConvLayer>&) { *st = nullptr; set_error("bf16 encoder path not built"); return AA_ERR_UNSUPPORTED; }
-void tc_destroy(TcState*) {}
-void tc_invalidate_weights(TcState*) {}
-int64_t tc_workspace_bytes(const std::vector<ConvLayer>&, int64_t, int64_t) { return 256; }
-int tc_forward(TcState*, const std::vector<ConvLayer>&, const std::vector<float*>&, const std::vector<float*>&, const float* const*,
-               const float*, int, int64_t, int64_t, int, float*, void*, cudaStream_t) {
-  set_error("bf16 encoder path not built");
-  return AA_ERR_UNSUPPORTED;
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr int BM = 128;             // output positions per tile (UMMA M)
+constexpr int kMaxChunks = 64;      // K chunks per tile
+constexpr int kTcThreads = 192;     // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+
+struct TcArgs {
+  int n_chunks;                     // K chunks of BK channels per tile
+  short chunk_off[kMaxChunks];      // row offset of the A box for chunk q
+  short chunk_col[kMaxChunks];      // column (channel) coordinate of the A box for chunk q
+  int bn, n_tiles_n, m_tiles;       // N tile width, tiles along cout, tiles along rows (per batch element)
+  long long tiles;                  // batch * m_tiles * n_tiles_n
+  int lout, lpad, cout;             // valid output rows, rows to zero-fill up to, output channels
+  int stages;
+  const float* bias;
+  const __nv_bfloat16* res;         // residual [B][lout_stride][cout] or NULL
+  __nv_bfloat16* out;               // [B][lout_stride][cout] bf16 channels-last, or NULL
+  float* out_f32;                   // [B][cout][lout] fp32 channel-major (last layer), or NULL
+  long long out_row_stride;         // rows per batch element in `out` / `res`
+  int elu, tanh_out;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TC_DONE;\n"
+      "bra TC_WAIT;\n"
+      "TC_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100): dense rows of BK bf16,
+// 8-row swizzle atoms stacked along M/N.  BK = 64 -> 128-byte rows, SWIZZLE_128B, SBO = 1024 B;
+// BK = 32 -> 64-byte rows, SWIZZLE_64B, SBO = 512 B.  LBO is unused for swizzled K-major (set to 1).
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  constexpr uint64_t sbo = (BK == 64) ? (1024 >> 4) : (512 >> 4);
+  constexpr uint64_t layout = (BK == 64) ? 2 : 4;   // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                           // leading byte offset (>>4), bits [16,30)
+  d |= sbo << 32;                                   // stride byte offset (>>4), bits [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version 1 (Blackwell), bits [46,48)
+  d |= layout << 61;                                // layout type, bits [61,64)
+  return d;
+}
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+
+template <int BK>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  const uint32_t B_BYTES = (uint32_t)a.bn * BK * 2;
+  const uint32_t STAGE = A_BYTES + ((B_BYTES + 1023u) & ~1023u);
+  const uint32_t bars = base + (uint32_t)a.stages * STAGE;              // full[S], empty[S], tfull[2], tempty[2], tmem ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * a.stages + 2 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * a.stages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (2 * a.bn <= 32) ? 32 : (2 * a.bn <= 64 ? 64 : (2 * a.bn <= 128 ? 128 : (2 * a.bn <= 256 ? 256 : 512)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_per_b = a.m_tiles * a.n_tiles_n;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+        const int b = (int)(t / tiles_per_b);
+        const int r = (int)(t % tiles_per_b);
+        const int nt = r % a.n_tiles_n, mt = r / a.n_tiles_n;
+        const int m0 = mt * BM, n0 = nt * a.bn;
+        for (int q = 0; q < a.n_chunks; ++q) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+          const uint32_t sa = base + (uint32_t)s * STAGE;
+          tma_load_3d(sa, &tmA, full_bar(s), a.chunk_col[q], m0 + a.chunk_off[q], b);
+          tma_load_2d(sa + A_BYTES, &tmB, full_bar(s), q * BK, n0);
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.bn);
+        for (int q = 0; q < a.n_chunks; ++q) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)s * STAGE;
+          const uint64_t da = make_desc<BK>(sa), db = make_desc<BK>(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)   // 16 bf16 = 32 bytes along K inside the swizzle atom
+            umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (q | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(s));           // frees the smem stage when these MMAs retire
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));           // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 =====================
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int it = 0;
+    for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int b = (int)(t / tiles_per_b);
+      const int r = (int)(t % tiles_per_b);
+      const int nt = r % a.n_tiles_n, mt = r / a.n_tiles_n;
+      const int m = mt * BM + row_in_tile, n0 = nt * a.bn;
+      mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
+      const bool valid = m < a.lout, ztail = (m >= a.lout) && (m < a.lpad);
+      for (int c0 = 0; c0 < a.bn; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);   // warp-collective: every lane participates
+        if (a.out_f32 != nullptr) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < a.cout) {
+                float x = __uint_as_float(v[j]) + __ldg(a.bias + n);
+                if (a.elu) x = elu1(x);
+                if (a.tanh_out) x = tanhf(x);
+                a.out_f32[((long long)b * a.cout + n) * a.lout + m] = x;
+              }
+            }
+          }
+        } else if (valid || ztail) {
+          const long long rowoff = ((long long)b * a.out_row_stride + m) * a.cout + n0 + c0;
+          uint4 packed[4];
+          uint4 rres[4];
+          if (valid && a.res != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rres[g] = __ldg(reinterpret_cast<const uint4*>(a.res + rowoff) + g);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int j = g * 8 + h * 2;
+              float x0 = 0.f, x1 = 0.f;
+              if (valid) {
+                x0 = __uint_as_float(v[j]) + __ldg(a.bias + n0 + c0 + j);
+                x1 = __uint_as_float(v[j + 1]) + __ldg(a.bias + n0 + c0 + j + 1);
+                if (a.res != nullptr) {
+                  const uint32_t rw = (h == 0) ? rres[g].x : (h == 1) ? rres[g].y : (h == 2) ? rres[g].z : rres[g].w;
+                  __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw);
+                  x0 += __bfloat162float(rb.x);
+                  x1 += __bfloat162float(rb.y);
+                }
+                if (a.elu) { x0 = elu1(x0); x1 = elu1(x1); }
+              }
+              __nv_bfloat162 o = __floats2bfloat162_rn(x0, x1);
+              w[h] = *reinterpret_cast<uint32_t*>(&o);
+            }
+            packed[g] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(a.out + rowoff)[g] = packed[g];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- layer 0: fp32 stems [B][cin<=4][N] (fader-scaled sum) -> conv k (<=7), cout <= 32 -> ELU -> bf16 [B][N][cout] ----
+struct L0Args {
+  const float* x[4];
+  float fader[4];
+  int n_in, cin, cout, k, pad, n, lpad;
+  const float* w;      // [cout][cin][k]
+  const float* bias;
+  __nv_bfloat16* out;  // [B][row_stride][cout]
+  long long row_stride;
+};
+__global__ void __launch_bounds__(256) conv_l0_kernel(const L0Args a) {
+  __shared__ float Xs[4][256 + 8];
+  __shared__ float Ws[32 * 4 * 7];
+  __shared__ float Bs[32];
+  const int b = blockIdx.y, l0 = blockIdx.x * 256;
+  for (int e = threadIdx.x; e < a.cout * a.cin * a.k; e += 256) Ws[e] = a.w[e];
+  if (threadIdx.x < a.cout) Bs[threadIdx.x] = a.bias[threadIdx.x];
+  const int span = 256 + a.k - 1;
+  for (int e = threadIdx.x; e < a.cin * span; e += 256) {
+    const int c = e / span, j = e % span, pos = l0 - a.pad + j;
+    float v = 0.f;
+    if (pos >= 0 && pos < a.n) {
+      const long long off = ((long long)b * a.cin + c) * a.n + pos;
+      v = a.fader[0] * a.x[0][off];
+      for (int s = 1; s < a.n_in; ++s) v = fmaf(a.fader[s], a.x[s][off], v);
+    }
+    Xs[c][j] = v;
+  }
+  __syncthreads();
+  const int l = l0 + threadIdx.x;
+  if (l >= a.lpad) return;
+  __nv_bfloat16* o = a.out + ((long long)b * a.row_stride + l) * a.cout;
+  for (int co0 = 0; co0 < a.cout; co0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = Bs[co0 + i];
+    for (int c = 0; c < a.cin; ++c)
+      for (int kk = 0; kk < a.k; ++kk) {
+        const float xv = Xs[c][threadIdx.x + kk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(Ws[((co0 + i) * a.cin + c) * a.k + kk], xv, acc[i]);
+      }
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float x0 = (l < a.n) ? elu1(acc[2 * i]) : 0.f, x1 = (l < a.n) ? elu1(acc[2 * i + 1]) : 0.f;
+      __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
+      w[i] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    *reinterpret_cast<uint4*>(o + co0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// W [cout][cin][k] fp32 -> W2 [cout][K_total] bf16 in chunk order: column (tap j, c) <- W[co][c % cin][c / cin + ktap_base[j]]
+struct PackArgs {
+  int n_taps, cin, k, cout, k_total;
+  int tap_col0[9], tap_width[9], tap_kbase[9], tap_kcol[9];
+};
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w2, const PackArgs p) {
+  const long long n = (long long)p.cout * p.k_total;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / p.k_total), kc = (int)(i % p.k_total);
+    int j = 0;
+    while (j + 1 < p.n_taps && kc >= p.tap_kcol[j + 1]) ++j;
+    const int c = p.tap_col0[j] + (kc - p.tap_kcol[j]);
+    const int ci = c % p.cin, kt = c / p.cin + p.tap_kbase[j];
+    w2[i] = __float2bfloat16((kt >= 0 && kt < p.k) ? w[((long long)co * p.cin + ci) * p.k + kt] : 0.f);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct LayerPlan {
+  int bk = 64;                 // K chunk (channels per TMA box)
+  int n_taps = 0;
+  int tap_off[9], tap_col0[9], tap_width[9], tap_kbase[9];
+  int view_c = 0;              // channels per row of the input view (s * cin)
+  int view_s = 1;              // positions per row of the input view
+  int k_total = 0;
+  __nv_bfloat16* w2 = nullptr;
+};
+
+}  // namespace
+
+namespace aa {
+
+struct TcState {
+  std::vector<LayerPlan> plans;
+  bool weights_valid = false;
+  int max_smem = 0;
+};
+
+static int plan_layer(const ConvLayer& l, LayerPlan& p) {
+  p = LayerPlan();
+  if (l.stride == 1) {
+    p.view_s = 1; p.view_c = l.cin; p.n_taps = l.k;
+    AA_REQUIRE(l.k <= 9, "kernel size %d not supported on the tensor-core path", l.k);
+    for (int j = 0; j < l.k; ++j) { p.tap_off[j] = j * l.dil - l.pad; p.tap_col0[j] = 0; p.tap_width[j] = l.cin; p.tap_kbase[j] = j; }
+  } else {
+    const int s = l.stride, pd = l.pad;
+    AA_REQUIRE(l.k == 2 * s && pd == (s + 1) / 2 && l.dil == 1 && s % 2 == 0, "strided conv shape not supported on the tensor-core path");
+    p.view_s = s; p.view_c = s * l.cin; p.n_taps = 3;
+    p.tap_off[0] = -1; p.tap_col0[0] = (s - pd) * l.cin; p.tap_width[0] = pd * l.cin;       p.tap_kbase[0] = -(s - pd);
+    p.tap_off[1] = 0;  p.tap_col0[1] = 0;               p.tap_width[1] = s * l.cin;        p.tap_kbase[1] = pd;
+    p.tap_off[2] = 1;  p.tap_col0[2] = 0;               p.tap_width[2] = (s - pd) * l.cin; p.tap_kbase[2] = pd + s;
+  }
+  p.bk = 64;
+  for (int j = 0; j < p.n_taps; ++j) if (p.tap_width[j] % 64 != 0) p.bk = 32;
+  p.k_total = 0;
+  for (int j = 0; j < p.n_taps; ++j) {
+    AA_REQUIRE(p.tap_width[j] % p.bk == 0 && p.tap_col0[j] % p.bk == 0, "channel count %d not a multiple of 32", l.cin);
+    p.k_total += p.tap_width[j];
+  }
+  AA_REQUIRE(p.k_total / p.bk <= kMaxChunks, "too many K chunks (%d)", p.k_total / p.bk);
+  AA_REQUIRE(l.cout % 32 == 0, "cout=%d must be a multiple of 32 on the tensor-core path", l.cout);
+  return AA_OK;
+}
+
+int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
+  AA_REQUIRE(get_encode_fn() != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  AA_REQUIRE(layers.size() >= 2 && layers[0].stride == 1 && layers[0].cout <= 32 && layers[0].cout % 8 == 0 && layers[0].cin <= 4 &&
+                 layers[0].k <= 7,
+             "first layer shape not supported on the tensor-core path");
+  TcState* st = new TcState();
+  st->plans.resize(layers.size());
+  for (size_t i = 1; i < layers.size(); ++i) {
+    int rc = plan_layer(layers[i], st->plans[i]);
+    if (rc != AA_OK) { delete st; return rc; }
+    AA_CUDA(cudaMalloc(&st->plans[i].w2, sizeof(__nv_bfloat16) * (size_t)layers[i].cout * st->plans[i].k_total));
+  }
+  int dev = 0;
+  AA_CUDA(cudaGetDevice(&dev));
+  AA_CUDA(cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  *out = st;
+  return AA_OK;
+}
+
+void tc_destroy(TcState* st) {
+  if (!st) return;
+  for (auto& p : st->plans) cudaFree(p.w2);
+  delete st;
+}
+
+void tc_invalidate_weights(TcState* st) { if (st) st->weights_valid = false; }
+
+static int64_t rows_padded(int64_t l) { return (l + 3) / 4 * 4; }
+
+static int64_t tc_max_act_elems(const std::vector<ConvLayer>& layers, int64_t batch, int64_t n) {
+  int64_t l = n, mx = 0;
+  for (const auto& ly : layers) {
+    const int64_t lout = (l + 2 * ly.pad - (int64_t)ly.dil * (ly.k - 1) - 1) / ly.stride + 1;
+    mx = std::max(mx, batch * rows_padded(lout) * ly.cout);
+    l = lout;
+  }
+  return mx;
+}
+
+int64_t tc_workspace_bytes(const std::vector<ConvLayer>& layers, int64_t batch, int64_t n) {
+  return 3 * (tc_max_act_elems(layers, batch, n) * 2 + 1024) + 1024;
+}
+
+int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vector<float*>& w, const std::vector<float*>& bvec,
+               const float* const* stems_host, const float* faders_host, int n_stems, int64_t batch, int64_t n, int apply_tanh,
+               float* y, void* workspace, cudaStream_t stream) {
+  AA_REQUIRE(batch < (1LL << 24) && n < (1LL << 30), "problem too large");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!st->weights_valid) {
+    for (size_t i = 1; i < layers.size(); ++i) {
+      const auto& ly = layers[i];
+      const LayerPlan& p = st->plans[i];
+      PackArgs pa{};
+      pa.n_taps = p.n_taps; pa.cin = ly.cin; pa.k = ly.k; pa.cout = ly.cout; pa.k_total = p.k_total;
+      int kc = 0;
+      for (int j = 0; j < p.n_taps; ++j) {
+        pa.tap_col0[j] = p.tap_col0[j]; pa.tap_width[j] = p.tap_width[j]; pa.tap_kbase[j] = p.tap_kbase[j]; pa.tap_kcol[j] = kc;
+        kc += p.tap_width[j];
+      }
+      const long long tot = (long long)ly.cout * p.k_total;
+      pack_weights_kernel<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, stream>>>(w[i], p.w2, pa);
+      AA_LAUNCH_CHECK();
+    }
+    st->weights_valid = true;
+  }
+  const int64_t buf_bytes = tc_max_act_elems(layers, batch, n) * 2 + 1024;
+  unsigned char* wsb = reinterpret_cast<unsigned char*>(workspace);
+  wsb += (1024 - (reinterpret_cast<uintptr_t>(wsb) & 1023)) & 1023;
+  __nv_bfloat16* buf[3] = {reinterpret_cast<__nv_bfloat16*>(wsb), reinterpret_cast<__nv_bfloat16*>(wsb + buf_bytes),
+                           reinterpret_cast<__nv_bfloat16*>(wsb + 2 * buf_bytes)};
+  int cur = 0, res_buf = -1;
+  int64_t l = n;
+  {  // ---- layer 0 on CUDA cores ----
+    const auto& ly = layers[0];
+    const int64_t lout = (l + 2 * ly.pad - (int64_t)ly.dil * (ly.k - 1) - 1) / ly.stride + 1;
+    AA_REQUIRE(lout == l && ly.dil == 1, "first layer must be a 'same' convolution");
+    L0Args a{};
+    a.n_in = n_stems;
+    for (int s = 0; s < n_stems; ++s) { a.x[s] = stems_host[s]; a.fader[s] = faders_host ? faders_host[s] : 1.0f; }
+    a.cin = ly.cin; a.cout = ly.cout; a.k = ly.k; a.pad = ly.pad; a.n = (int)n; a.lpad = (int)rows_padded(lout);
+    a.w = w[0]; a.bias = bvec[0]; a.out = buf[0]; a.row_stride = rows_padded(lout);
+    conv_l0_kernel<<<dim3((unsigned)((a.lpad + 255) / 256), (unsigned)batch), 256, 0, stream>>>(a);
+    AA_LAUNCH_CHECK();
+    l = lout;
+  }
+  for (size_t i = 1; i < layers.size(); ++i) {
+    const auto& ly = layers[i];
+    const LayerPlan& p = st->plans[i];
+    const int64_t lout = (l + 2 * ly.pad - (int64_t)ly.dil * (ly.k - 1) - 1) / ly.stride + 1;
+    AA_REQUIRE(lout >= 1, "input too short for layer %zu", i);
+    const bool last = (i + 1 == layers.size());
+    int dst = 0;
+    while (dst == cur || dst == res_buf) ++dst;
+    if (ly.role == ROLE_RES_FIRST) res_buf = cur;
+    const int64_t in_rows_alloc = rows_padded(l);                 // rows per batch element of the input buffer
+    const int64_t view_rows = (l + p.view_s - 1) / p.view_s;      // rows of the (possibly strided) view
+    // ---- tensor maps ----
+    CUtensorMap tmA, tmB;
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)p.view_c, (cuuint64_t)view_rows, (cuuint64_t)batch};
+      cuuint64_t strides[2] = {(cuuint64_t)p.view_c * 2, (cuuint64_t)in_rows_alloc * ly.cin * 2};
+      cuuint32_t box[3] = {(cuuint32_t)p.bk, (cuuint32_t)BM, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, buf[cur], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed for layer %zu: %d", i, (int)r);
+    }
+    const int bn = std::min(ly.cout, 256);
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)p.k_total, (cuuint64_t)ly.cout};
+      cuuint64_t strides[1] = {(cuuint64_t)p.k_total * 2};
+      cuuint32_t box[2] = {(cuuint32_t)p.bk, (cuuint32_t)bn};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.w2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed for layer %zu: %d", i, (int)r);
+    }
+    TcArgs a{};
+    a.n_chunks = 0;
+    for (int j = 0; j < p.n_taps; ++j)
+      for (int c = 0; c < p.tap_width[j]; c += p.bk) {
+        a.chunk_off[a.n_chunks] = (short)p.tap_off[j];
+        a.chunk_col[a.n_chunks] = (short)(p.tap_col0[j] + c);
+        ++a.n_chunks;
+      }
+    a.bn = bn; a.n_tiles_n = ly.cout / bn; a.m_tiles = (int)((rows_padded(lout) + BM - 1) / BM);
+    a.tiles = batch * a.m_tiles * a.n_tiles_n;
+    a.lout = (int)lout; a.lpad = (int)rows_padded(lout); a.cout = ly.cout;
+    a.bias = bvec[i];
+    a.res = (ly.role == ROLE_RES_SECOND) ? buf[res_buf] : nullptr;
+    a.out = last ? nullptr : buf[dst];
+    a.out_f32 = last ? y : nullptr;
+    a.out_row_stride = rows_padded(lout);
+    a.elu = ly.elu; a.tanh_out = (last && apply_tanh) ? 1 : 0;
+    const int stage_bytes = BM * p.bk * 2 + ((bn * p.bk * 2 + 1023) & ~1023);
+    a.stages = std::max(2, std::min(8, (st->max_smem - 2048) / stage_bytes));
+    const int smem = a.stages * stage_bytes + 1024 + 256;
+    const int grid = (int)std::min<long long>(a.tiles, aa::num_sms());
+    if (p.bk == 64) conv_tc_kernel<64><<<grid, kTcThreads, smem, stream>>>(tmA, tmB, a);
+    else conv_tc_kernel<32><<<grid, kTcThreads, smem, stream>>>(tmA, tmB, a);
+    AA_LAUNCH_CHECK();
+    if (ly.role == ROLE_RES_SECOND) res_buf = -1;
+    cur = dst;
+    l = lout;
+  }
+  return AA_OK;
+}
+
 }  // namespace aa
