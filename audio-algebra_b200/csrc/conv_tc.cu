@@ -26,7 +26,9 @@ namespace {
 
 constexpr int BM = 128;             // output positions per tile (UMMA M)
 constexpr int kMaxChunks = 64;      // K chunks per tile
-constexpr int kTcThreads = 192;     // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+constexpr int kMaxEpi = 4;          // epilogue warp groups (4 warps each); warp 0: TMA, warp 1: MMA
+constexpr int kTcMaxThreads = 64 + 128 * kMaxEpi;
+constexpr int kMaxAcc = 8;
 
 struct TcArgs {
   int n_chunks;                     // K chunks of BK channels per tile
@@ -36,6 +38,7 @@ struct TcArgs {
   long long tiles;                  // batch * m_tiles * n_tiles_n
   int lout, lpad, cout;             // valid output rows, rows to zero-fill up to, output channels
   int stages;
+  int n_acc, n_epi;                 // TMEM accumulator buffers, epilogue warp groups (tile i -> buffer i % n_acc, group i % n_epi)
   const float* bias;
   const __nv_bfloat16* res;         // residual [B][lout_stride][cout] or NULL
   __nv_bfloat16* out;               // [B][lout_stride][cout] bf16 channels-last, or NULL
@@ -123,28 +126,30 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+// ELU(alpha = 1), branch free; ex2.approx error (~2^-22 relative on exp) is far below the bf16 output precision
+__device__ __forceinline__ float elu1(float v) { return fmaxf(v, 0.f) + (__expf(fminf(v, 0.f)) - 1.0f); }
 
 template <int BK>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
   constexpr uint32_t A_BYTES = BM * BK * 2;
   const uint32_t B_BYTES = (uint32_t)a.bn * BK * 2;
   const uint32_t STAGE = A_BYTES + ((B_BYTES + 1023u) & ~1023u);
-  const uint32_t bars = base + (uint32_t)a.stages * STAGE;              // full[S], empty[S], tfull[2], tempty[2], tmem ptr
+  const uint32_t bars = base + (uint32_t)a.stages * STAGE;              // full[S], empty[S], tfull[8], tempty[8], tmem ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
-  auto tempty_bar = [&](int i) { return bars + 8u * (2 * a.stages + 2 + i); };
-  const uint32_t tmem_slot = bars + 8u * (2 * a.stages + 4);
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * a.stages + kMaxAcc + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * a.stages + 2 * kMaxAcc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (2 * a.bn <= 32) ? 32 : (2 * a.bn <= 64 ? 64 : (2 * a.bn <= 128 ? 128 : (2 * a.bn <= 256 ? 256 : 512)));
+  const int acc_cols = a.n_acc * a.bn;
+  const uint32_t tmem_cols = (acc_cols <= 32) ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    for (int i = 0; i < a.n_acc; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -161,7 +166,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
   const int tiles_per_b = a.m_tiles * a.n_tiles_n;
 
-  if (warp == 0) {
+  if (warp >= 2 + 4 * a.n_epi) {
+    // unused epilogue warps of this launch configuration
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
@@ -190,8 +197,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       uint32_t ph = 0;
       int it = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        const int acc = it % a.n_acc;
+        mbar_wait(tempty_bar(acc), (((uint32_t)(it / a.n_acc)) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.bn);
         for (int q = 0; q < a.n_chunks; ++q) {
@@ -210,55 +217,93 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
   } else {
     // ===================== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 =====================
-    const int quarter = warp & 3;
+    // The [128 x bn] bf16 output tile is staged in shared memory (rows padded by 16 B -> conflict-free) so that
+    // the residual is read and the result written with fully coalesced 16-byte accesses.
+    const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;                       // epilogue group
     const int row_in_tile = quarter * 32 + lane;
+    const int et = (threadIdx.x - 64) & 127;               // 0..127 within the group
+    const uint32_t RS = (uint32_t)a.bn * 2u + 16u;         // row stride in bytes
+    const uint32_t grp_bytes = (a.out_f32 == nullptr ? (uint32_t)BM * RS : 0u) + (uint32_t)a.bn * 4u;
+    const uint32_t stg = bars + 512u + (uint32_t)grp * grp_bytes;   // this group's staging area, then its bias copy
+    const int vec_per_row = a.bn / 8;                      // 16-byte vectors per row (power of two)
+    const int vpr_shift = 31 - __clz(vec_per_row);
+    const uint32_t sbias = stg + (a.out_f32 == nullptr ? (uint32_t)BM * RS : 0u);   // bn floats
+    const int bar_id = 1 + grp;
+    int bias_n0 = -1;
     int it = 0;
     for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
+      if (it % a.n_epi != grp) continue;
+      const int acc = it % a.n_acc;
       const int b = (int)(t / tiles_per_b);
       const int r = (int)(t % tiles_per_b);
       const int nt = r % a.n_tiles_n, mt = r / a.n_tiles_n;
-      const int m = mt * BM + row_in_tile, n0 = nt * a.bn;
-      mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u);
+      const int m0 = mt * BM, n0 = nt * a.bn;
+      const int m = m0 + row_in_tile;
+      const bool valid = m < a.lout;
+      const long long tile_off = ((long long)b * a.out_row_stride + m0) * a.cout + n0;   // element offset of (row 0, col 0)
+      if (n0 != bias_n0) {                                  // (re)load this N tile's bias into shared memory
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        for (int i = et; i < a.bn; i += 128) {
+          const float bv = (n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * i), "f"(bv) : "memory");
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        bias_n0 = n0;
+      }
+      if (a.out_f32 == nullptr && a.res != nullptr) {       // residual tile -> staging (overlaps with the MMAs)
+        for (int idx = et; idx < BM * vec_per_row; idx += 128) {
+          const int rr = idx >> vpr_shift, cv = idx & (vec_per_row - 1);
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (m0 + rr < a.lout) v = __ldg(reinterpret_cast<const uint4*>(a.res + tile_off + (long long)rr * a.cout) + cv);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)rr * RS + (uint32_t)cv * 16u), "r"(v.x),
+                       "r"(v.y), "r"(v.z), "r"(v.w)
+                       : "memory");
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
+      mbar_wait(tfull_bar(acc), ((uint32_t)(it / a.n_acc)) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
-      const bool valid = m < a.lout, ztail = (m >= a.lout) && (m < a.lpad);
       for (int c0 = 0; c0 < a.bn; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);   // warp-collective: every lane participates
+        float bia[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bia[j]), "=f"(bia[j + 1]), "=f"(bia[j + 2]), "=f"(bia[j + 3])
+                       : "r"(sbias + 4u * (uint32_t)(c0 + j)));
         if (a.out_f32 != nullptr) {
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = n0 + c0 + j;
               if (n < a.cout) {
-                float x = __uint_as_float(v[j]) + __ldg(a.bias + n);
+                float x = __uint_as_float(v[j]) + bia[j];
                 if (a.elu) x = elu1(x);
                 if (a.tanh_out) x = tanhf(x);
                 a.out_f32[((long long)b * a.cout + n) * a.lout + m] = x;
               }
             }
           }
-        } else if (valid || ztail) {
-          const long long rowoff = ((long long)b * a.out_row_stride + m) * a.cout + n0 + c0;
-          uint4 packed[4];
-          uint4 rres[4];
-          if (valid && a.res != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) rres[g] = __ldg(reinterpret_cast<const uint4*>(a.res + rowoff) + g);
-          }
+        } else {
+          const uint32_t srow = stg + (uint32_t)row_in_tile * RS + (uint32_t)c0 * 2u;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
+            uint4 rres = make_uint4(0u, 0u, 0u, 0u);
+            if (a.res != nullptr)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres.x), "=r"(rres.y), "=r"(rres.z), "=r"(rres.w)
+                           : "r"(srow + (uint32_t)g * 16u));
             uint32_t w[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const int j = g * 8 + h * 2;
               float x0 = 0.f, x1 = 0.f;
               if (valid) {
-                x0 = __uint_as_float(v[j]) + __ldg(a.bias + n0 + c0 + j);
-                x1 = __uint_as_float(v[j + 1]) + __ldg(a.bias + n0 + c0 + j + 1);
+                x0 = __uint_as_float(v[j]) + bia[j];
+                x1 = __uint_as_float(v[j + 1]) + bia[j + 1];
                 if (a.res != nullptr) {
-                  const uint32_t rw = (h == 0) ? rres[g].x : (h == 1) ? rres[g].y : (h == 2) ? rres[g].z : rres[g].w;
+                  const uint32_t rw = (h == 0) ? rres.x : (h == 1) ? rres.y : (h == 2) ? rres.z : rres.w;
                   __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw);
                   x0 += __bfloat162float(rb.x);
                   x1 += __bfloat162float(rb.y);
@@ -268,15 +313,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               __nv_bfloat162 o = __floats2bfloat162_rn(x0, x1);
               w[h] = *reinterpret_cast<uint32_t*>(&o);
             }
-            packed[g] = make_uint4(w[0], w[1], w[2], w[3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)g * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                         "r"(w[3])
+                         : "memory");
           }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(a.out + rowoff)[g] = packed[g];
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive(tempty_bar(acc));          // accumulator drained: the MMA warp may reuse it
+      if (a.out_f32 == nullptr) {
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // tile complete in staging
+        for (int idx = et; idx < BM * vec_per_row; idx += 128) {
+          const int rr = idx >> vpr_shift, cv = idx & (vec_per_row - 1);
+          if (m0 + rr < a.lpad) {                           // rows in [lout, lpad) carry zeros (tail of a strided view)
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(stg + (uint32_t)rr * RS + (uint32_t)cv * 16u));
+            reinterpret_cast<uint4*>(a.out + tile_off + (long long)rr * a.cout)[cv] = v;
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // staging free for the next tile
+      }
     }
   }
 
@@ -317,9 +375,11 @@ __global__ void __launch_bounds__(256) conv_l0_kernel(const L0Args a) {
     Xs[c][j] = v;
   }
   __syncthreads();
+  // results are staged in shared memory (row stride cout*2 + 16 bytes: conflict-free) and written as one
+  // contiguous, fully coalesced block: 256 positions x cout channels are adjacent in the channels-last layout
+  __shared__ __align__(16) unsigned char Os[256 * (32 * 2 + 16)];
   const int l = l0 + threadIdx.x;
-  if (l >= a.lpad) return;
-  __nv_bfloat16* o = a.out + ((long long)b * a.row_stride + l) * a.cout;
+  const int RS = a.cout * 2 + 16;
   for (int co0 = 0; co0 < a.cout; co0 += 8) {
     float acc[8];
 #pragma unroll
@@ -337,7 +397,14 @@ __global__ void __launch_bounds__(256) conv_l0_kernel(const L0Args a) {
       __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
       w[i] = *reinterpret_cast<uint32_t*>(&p);
     }
-    *reinterpret_cast<uint4*>(o + co0) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(Os + threadIdx.x * RS + co0 * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+  const int vpr = a.cout / 8;
+  uint4* o = reinterpret_cast<uint4*>(a.out + ((long long)b * a.row_stride + l0) * a.cout);
+  for (int idx = threadIdx.x; idx < 256 * vpr; idx += 256) {
+    const int rr = idx / vpr, cv = idx - rr * vpr;
+    if (l0 + rr < a.lpad) o[idx] = *reinterpret_cast<const uint4*>(Os + rr * RS + cv * 16);
   }
 }
 
@@ -530,7 +597,9 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed for layer %zu: %d", i, (int)r);
     }
-    const int bn = std::min(ly.cout, 256);
+    const int n_chunks_total = p.k_total / p.bk;
+    // K-light layers (1x1 convs) are epilogue bound: narrower N tiles and more epilogue groups in flight
+    const int bn = std::min(ly.cout, (n_chunks_total <= 8 && !last) ? 128 : 256);
     {
       cuuint64_t dims[2] = {(cuuint64_t)p.k_total, (cuuint64_t)ly.cout};
       cuuint64_t strides[1] = {(cuuint64_t)p.k_total * 2};
@@ -559,11 +628,16 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     a.out_row_stride = rows_padded(lout);
     a.elu = ly.elu; a.tanh_out = (last && apply_tanh) ? 1 : 0;
     const int stage_bytes = BM * p.bk * 2 + ((bn * p.bk * 2 + 1023) & ~1023);
-    a.stages = std::max(2, std::min(8, (st->max_smem - 2048) / stage_bytes));
-    const int smem = a.stages * stage_bytes + 1024 + 256;
+    a.n_epi = last ? 1 : (bn <= 64 ? 4 : (bn <= 128 ? 2 : 1));
+    a.n_acc = std::min(kMaxAcc, std::min(512 / bn, 2 * a.n_epi));
+    const int staging = a.n_epi * ((last ? 0 : BM * (bn * 2 + 16)) + bn * 4);
+    a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging) / stage_bytes));
+    const int smem = a.stages * stage_bytes + 1024 + 512 + staging;
+    AA_REQUIRE(smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);
     const int grid = (int)std::min<long long>(a.tiles, aa::num_sms());
-    if (p.bk == 64) conv_tc_kernel<64><<<grid, kTcThreads, smem, stream>>>(tmA, tmB, a);
-    else conv_tc_kernel<32><<<grid, kTcThreads, smem, stream>>>(tmA, tmB, a);
+    const int threads = 64 + 128 * a.n_epi;
+    if (p.bk == 64) conv_tc_kernel<64><<<grid, threads, smem, stream>>>(tmA, tmB, a);
+    else conv_tc_kernel<32><<<grid, threads, smem, stream>>>(tmA, tmB, a);
     AA_LAUNCH_CHECK();
     if (ly.role == ROLE_RES_SECOND) res_buf = -1;
     cur = dst;
