@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -128,6 +129,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 
 // ELU(alpha = 1), branch free; ex2.approx error (~2^-22 relative on exp) is far below the bf16 output precision
 __device__ __forceinline__ float elu1(float v) { return fmaxf(v, 0.f) + (__expf(fminf(v, 0.f)) - 1.0f); }
+
+#include "conv_ru.cuh"
 
 template <int BK>
 __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -459,6 +462,8 @@ struct TcState {
   std::vector<LayerPlan> plans;
   bool weights_valid = false;
   int max_smem = 0;
+  bool fuse_ru = true;          // ResidualUnits with C = 32 / 64 run as one fused kernel (conv_ru.cuh)
+  int ru_ctas_per_sm[2] = {1, 1};
 };
 
 static int plan_layer(const ConvLayer& l, LayerPlan& p) {
@@ -504,6 +509,11 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<32>::SMEM));
+  AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<64>::SMEM));
+  AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[0], ru_fused_kernel<32>, kRuThreads, RuCfg<32>::SMEM));
+  AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[1], ru_fused_kernel<64>, kRuThreads, RuCfg<64>::SMEM));
+  st->fuse_ru = getenv("AA_NO_RU_FUSION") == nullptr;
   *out = st;
   return AA_OK;
 }
@@ -582,6 +592,30 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     const bool last = (i + 1 == layers.size());
     int dst = 0;
     while (dst == cur || dst == res_buf) ++dst;
+    // ---- fused ResidualUnit: k7 (dilated) conv -> ELU -> 1x1 conv -> + x -> ELU in one kernel (conv_ru.cuh) ----
+    if (st->fuse_ru && ly.role == ROLE_RES_FIRST && i + 2 < layers.size() && layers[i + 1].role == ROLE_RES_SECOND && ly.k == 7 &&
+        ly.stride == 1 && ly.cin == ly.cout && (ly.cin == 32 || ly.cin == 64) && ly.pad == 3 * ly.dil && ly.dil <= 9 && ly.elu &&
+        layers[i + 1].k == 1 && layers[i + 1].stride == 1 && layers[i + 1].cin == ly.cin && layers[i + 1].cout == ly.cin &&
+        layers[i + 1].elu && lout == l) {
+      RuArgs ra{};
+      ra.x = buf[cur]; ra.out = buf[dst];
+      ra.w7 = p.w2; ra.w1 = st->plans[i + 1].w2; ra.b7 = bvec[i]; ra.b1 = bvec[i + 1];
+      ra.lout = (int)lout; ra.lpad = (int)rows_padded(lout); ra.dil = ly.dil;
+      ra.m_tiles = (int)((rows_padded(lout) + BM - 1) / BM);
+      ra.rows_alloc = rows_padded(l); ra.tiles = batch * ra.m_tiles;
+      if (ly.cin == 32) {
+        const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms() * st->ru_ctas_per_sm[0]);
+        ru_fused_kernel<32><<<grid, kRuThreads, RuCfg<32>::SMEM, stream>>>(ra);
+      } else {
+        const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms() * st->ru_ctas_per_sm[1]);
+        ru_fused_kernel<64><<<grid, kRuThreads, RuCfg<64>::SMEM, stream>>>(ra);
+      }
+      AA_LAUNCH_CHECK();
+      cur = dst;
+      l = lout;
+      ++i;   // the 1x1 layer is part of the fused kernel
+      continue;
+    }
     if (ly.role == ROLE_RES_FIRST) res_buf = cur;
     const int64_t in_rows_alloc = rows_padded(l);                 // rows per batch element of the input buffer
     const int64_t view_rows = (l + p.view_s - 1) / p.view_s;      // rows of the (possibly strided) view

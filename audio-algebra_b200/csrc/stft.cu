@@ -54,7 +54,7 @@ struct StftArgs {
   float* out;
   int wav_aligned16;
   long long n_tiles;      // fast path: row pairs x tiles_per_pair
-  const int4* mel_steps;  // fast path: [kWarps][mel_steps_per_warp][2] step headers, then the step weights
+  const int4* mel_steps;  // fast path: [kWarps][mel_steps_per_warp + 1][4] step headers, then the step weights
   int mel_steps_per_warp, mel_hdr_bytes, mel_w_bytes;
   const float* lane_consts;  // fast path: float4[32] Hann phases + float2[32] W_2048^lane
 };
@@ -85,6 +85,16 @@ constexpr int kCStride = 260;                   // complex-mode staging: [12 lin
 static_assert(kPLine >= 1028, "a P line (1025 bins + pad) must fit in one exchange buffer");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
   float2* s_tw1 = reinterpret_cast<float2*>(stage + kStageBytes);    // [32][32] W_1024^(k1 n2)
   float4* s_lane = reinterpret_cast<float4*>(s_tw1 + 1024);          // [32] (cos,sin) of 2pi(2 lane + {0,1})/2048
   float2* s_tw2l = reinterpret_cast<float2*>(s_lane + 32);           // [32] W_2048^lane
-  int4* s_melh = reinterpret_cast<int4*>(s_tw2l + 32);               // mel step headers [kWarps][steps][2]
+  int4* s_melh = reinterpret_cast<int4*>(s_tw2l + 32);               // mel step headers [kWarps][steps + 1][4 quarter-warps]
   float4* s_melw = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s_melh) + a.mel_hdr_bytes);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_melw) + a.mel_w_bytes);
   constexpr bool kPrefetch = (MODE != MODE_COMPLEX);  // complex mode reuses the sample area as staging
@@ -435,35 +445,54 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
         // packed (rowA,rowB) FFMA2.
         const int q = lane >> 3, fl = lane & 7;
         const bool factive = fl < kWarps;
-        const float4* pf = reinterpret_cast<const float4*>(P + (factive ? fl : 0) * kPLine);
-        const bool store_ok = factive && (f0 + fl < a.n_frames);
-        const bool hasB = rowA + 1 < a.rows;
         // 32-bit output indexing (the host routes outputs of >= 2^31 elements to the generic kernel)
-        const int plane_sz = a.n_mels * a.n_frames;
-        const int obase = (int)rowA * plane_sz + f0 + fl;
-        const int4* steps = s_melh + warp * a.mel_steps_per_warp * 2;
+        unsigned plane_sz = (unsigned)a.n_mels * (unsigned)a.n_frames;
+        unsigned n_frames_u = (unsigned)a.n_frames;
+        float* outA = a.out + (size_t)rowA * plane_sz + (f0 + fl);
+        // bit 0: this lane stores row A, bit 1: row B exists
+        unsigned flags = ((factive && (f0 + fl < a.n_frames)) ? 1u : 0u) | ((rowA + 1 < a.rows) ? 2u : 0u);
+        // shared-window addresses of this lane's P line, the step weights and this quarter-warp's header list:
+        // per-(warp, step, quarter) header {P offset (bytes), n_iter / 2, weight offset (bytes), filter or -1};
+        // the list of a warp ends with an n_iter = 0 entry
+        unsigned pf = smem_u32(P + (factive ? fl : 0) * kPLine);
+        unsigned wbase = smem_u32(s_melw);
+        unsigned hp = smem_u32(s_melh + warp * (a.mel_steps_per_warp + 1) * 4 + q);
+        // keep the loop invariants in registers (otherwise they are rematerialised in every step)
+        asm volatile("" : "+r"(plane_sz), "+r"(n_frames_u), "+l"(outA), "+r"(flags), "+r"(pf), "+r"(wbase), "+r"(hp));
+        int4 h = lds_i4(hp);
 #pragma unroll 1
-        for (int st = 0; st < a.mel_steps_per_warp; ++st) {
-          const int4 h1 = steps[2 * st + 1];   // {n_iter (even), weight offset, first filter, filters in step}
-          if (h1.w == 0) break;
-          const int bin0 = reinterpret_cast<const int*>(steps + 2 * st)[q];
-          const float4* wq = s_melw + h1.y + q;
-          const float4* pp = pf + (bin0 >> 1);
-          float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 2
-          for (int it = 0; it < h1.x; ++it) {
-            const float4 w = wq[4 * it];
-            const float4 p0 = pp[2 * it], p1 = pp[2 * it + 1];
+        while (h.y != 0) {
+          hp += 64;
+          const int4 hn = lds_i4(hp);   // next step's header: its latency hides behind this step's loop
+          unsigned wq = wbase + (unsigned)h.z;
+          unsigned pp = pf + (unsigned)h.x;
+          // four independent accumulation chains (one per bin of the float4 group); loads run one
+          // iteration ahead of the FFMA2s (the loop is load-latency bound)
+          float2 acc = make_float2(0.f, 0.f), acc1 = acc, acc2 = acc, acc3 = acc;
+          float4 w = lds_f4(wq), p0 = lds_f4(pp), p1 = lds_f4(pp + 16);
+          int it = h.y;   // pairs of iterations (the host pads every step to an even count)
+#pragma unroll 1
+          do {
+            const float4 wb = lds_f4(wq + 64), p0b = lds_f4(pp + 32), p1b = lds_f4(pp + 48);
             acc = pfma(make_float2(p0.x, p0.y), w.x, acc);
-            acc = pfma(make_float2(p0.z, p0.w), w.y, acc);
-            acc = pfma(make_float2(p1.x, p1.y), w.z, acc);
-            acc = pfma(make_float2(p1.z, p1.w), w.w, acc);
+            acc1 = pfma(make_float2(p0.z, p0.w), w.y, acc1);
+            acc2 = pfma(make_float2(p1.x, p1.y), w.z, acc2);
+            acc3 = pfma(make_float2(p1.z, p1.w), w.w, acc3);
+            wq += 128;
+            pp += 64;
+            w = lds_f4(wq); p0 = lds_f4(pp); p1 = lds_f4(pp + 16);   // over-read past the last pair stays in smem
+            acc = pfma(make_float2(p0b.x, p0b.y), wb.x, acc);
+            acc1 = pfma(make_float2(p0b.z, p0b.w), wb.y, acc1);
+            acc2 = pfma(make_float2(p1b.x, p1b.y), wb.z, acc2);
+            acc3 = pfma(make_float2(p1b.z, p1b.w), wb.w, acc3);
+          } while (--it);
+          acc = padd(padd(acc, acc1), padd(acc2, acc3));
+          if ((flags & 1u) && h.w >= 0) {
+            float* o = outA + (unsigned)h.w * n_frames_u;
+            asm volatile("st.global.f32 [%0], %1;" ::"l"(o), "f"(acc.x) : "memory");
+            if (flags & 2u) asm volatile("st.global.f32 [%0], %1;" ::"l"(o + plane_sz), "f"(acc.y) : "memory");
           }
-          if (store_ok && q < h1.w) {
-            const int idx = obase + (h1.z + q) * a.n_frames;
-            a.out[idx] = acc.x;
-            if (hasB) a.out[idx + plane_sz] = acc.y;
-          }
+          h = hn;
         }
       } else {  // MODE_POWER: lanes = (32 bins) x (6 frames) -> 24-byte runs along the frame axis
         const int fsub = tid % kWarps, ksub = tid / kWarps;
@@ -750,12 +779,17 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
       }
       size_t spw = 1;
       for (auto& l : per_warp) spw = std::max(spw, l.size());
-      std::vector<int4> tab((size_t)kWarps * spw * 2, make_int4(0, 0, 0, 0));
+      // headers [kWarps][spw + 1][4 quarters] = {P offset in bytes (8 per bin), n_iter / 2, weight offset in bytes, filter or -1}
+      std::vector<int4> tab((size_t)kWarps * (spw + 1) * 4, make_int4(0, 0, 0, -1));
       for (int wq = 0; wq < kWarps; ++wq)
         for (size_t i = 0; i < per_warp[wq].size(); ++i) {
-          tab[((size_t)wq * spw + i) * 2] = steps[per_warp[wq][i]].h0;
-          tab[((size_t)wq * spw + i) * 2 + 1] = steps[per_warp[wq][i]].h1;
+          const Step& s = steps[per_warp[wq][i]];
+          const int b[4] = {s.h0.x, s.h0.y, s.h0.z, s.h0.w};
+          for (int qq = 0; qq < 4; ++qq)
+            tab[((size_t)wq * (spw + 1) + i) * 4 + qq] =
+                make_int4((b[qq] >> 1) * 16, s.h1.x / 2, (s.h1.y + qq) * 16, qq < s.h1.w ? s.h1.z + qq : -1);
         }
+      sw.resize(sw.size() + 32, 0.f);   // the device loop prefetches past the last step
       p->mel_steps_per_warp = (int)spw;
       p->mel_hdr_bytes = (int)(sizeof(int4) * tab.size());
       p->mel_w_bytes = (int)(sizeof(float) * sw.size());

@@ -108,3 +108,30 @@ def test_bf16_mode_cosine(setup):
     ref = O.dvae_encode(enc_o, f[0] * s0 + f[1] * s1).double()
     cos = torch.nn.functional.cosine_similarity(y.flatten(1), ref.flatten(1), dim=1)
     assert cos.min().item() >= 0.999, cos
+
+
+def test_bf16_fused_residual_units_match_layerwise(setup):
+    """The fused ResidualUnit kernel (conv_ru.cuh: k7 -> ELU -> k1 -> +x -> ELU in one tcgen05 kernel, C = 32 / 64) against
+    the layer-by-layer tcgen05 path (AA_NO_RU_FUSION=1 at handle creation): same bf16 operands, so the two agree to
+    accumulation-order / bf16 rounding noise -- a tap, dilation or row-offset mistake would show as O(1) error."""
+    import os
+    aab, O, enc_o, dv = setup
+
+    def make(no_fusion):
+        if no_fusion:
+            os.environ["AA_NO_RU_FUSION"] = "1"
+        try:
+            w = aab.DVAEWrapper(debug=False, compute_dtype="bf16")
+            w.model.load_oracle_weights(enc_o)
+            w = w.cuda()
+            w.encode(torch.zeros(1, 2, 1024, device="cuda"))   # the handle reads the switch at its first bf16 forward
+        finally:
+            os.environ.pop("AA_NO_RU_FUSION", None)
+        return w
+
+    fused, layerwise = make(False), make(True)
+    for shape, seed in [((2, 2, 16384), 21), ((3, 2, 5000), 22), ((1, 2, 131072), 23), ((5, 2, 640), 24), ((1, 2, 128), 25)]:
+        x = _x(shape, seed).cuda()
+        a, b = fused.encode(x), layerwise.encode(x)
+        assert tuple(a.shape) == tuple(b.shape)
+        assert rel_l2(a, b.cpu()) < 1.5e-2, (shape, rel_l2(a, b.cpu()))
