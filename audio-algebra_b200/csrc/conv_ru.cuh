@@ -20,7 +20,6 @@
 #pragma once
 
 constexpr int kRuThreads = 64 + 256;
-constexpr int kRuStages = 3;   // x tiles in flight
 
 struct RuArgs {
   const __nv_bfloat16* x;    // [B][rows_alloc][C] channels-last
@@ -49,7 +48,8 @@ struct RuCfg {
   static constexpr int OFF_W7 = 1024;
   static constexpr int OFF_W1 = OFF_W7 + W7BYTES;
   static constexpr int OFF_X = OFF_W1 + W1BYTES;
-  static constexpr int OFF_T = OFF_X + kRuStages * XBYTES;
+  static constexpr int NX = (C == 64) ? 4 : 6;           // x tiles in flight
+  static constexpr int OFF_T = OFF_X + NX * XBYTES;
   static constexpr int SMEM = OFF_T + 2 * TBYTES + 128;  // + alignment slack
   static constexpr int TMEM_COLS = 4 * C;                // {acc1, acc2} x 2 epilogue groups
 };
@@ -95,24 +95,24 @@ __device__ __forceinline__ void group_sync(int g) {
 template <int C>
 __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel(const RuArgs a) {
   using Cfg = RuCfg<C>;
-  constexpr int P = Cfg::P;
+  constexpr int P = Cfg::P, NX = Cfg::NX;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
-  // barriers: xfull[3] xempty[3] acc1full[2] acc1empty[2] tfull[2] acc2full[2] acc2empty[2], tmem slot
+  // barriers: xfull[NX] xempty[NX] acc1full[2] acc1empty[2] tfull[2] acc2full[2] acc2empty[2], tmem slot
   auto xfull = [&](int s) { return base + 8u * s; };
-  auto xempty = [&](int s) { return base + 8u * (3 + s); };
-  auto acc1full = [&](int g) { return base + 8u * (6 + g); };
-  auto acc1empty = [&](int g) { return base + 8u * (8 + g); };
-  auto tfull = [&](int g) { return base + 8u * (10 + g); };
-  auto acc2full = [&](int g) { return base + 8u * (12 + g); };
-  auto acc2empty = [&](int g) { return base + 8u * (14 + g); };
-  const uint32_t tmem_slot = base + 8u * 16;
+  auto xempty = [&](int s) { return base + 8u * (NX + s); };
+  auto acc1full = [&](int g) { return base + 8u * (2 * NX + g); };
+  auto acc1empty = [&](int g) { return base + 8u * (2 * NX + 2 + g); };
+  auto tfull = [&](int g) { return base + 8u * (2 * NX + 4 + g); };
+  auto acc2full = [&](int g) { return base + 8u * (2 * NX + 6 + g); };
+  auto acc2empty = [&](int g) { return base + 8u * (2 * NX + 8 + g); };
+  const uint32_t tmem_slot = base + 8u * (2 * NX + 10);
   const uint32_t sbias = base + Cfg::OFF_BIAS;   // b7[C], b1[C]
   const uint32_t sW7 = base + Cfg::OFF_W7, sW1 = base + Cfg::OFF_W1, sX = base + Cfg::OFF_X, sT = base + Cfg::OFF_T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRuStages; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 4); }
+    for (int s = 0; s < NX; ++s) { mbar_init(xfull(s), 32); mbar_init(xempty(s), 4); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(acc1full(g), 1); mbar_init(acc1empty(g), 4); mbar_init(tfull(g), 4);
       mbar_init(acc2full(g), 1); mbar_init(acc2empty(g), 4);
@@ -157,10 +157,9 @@ __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel
     const int pn = lane % P, r_lane = lane / P;
     constexpr int RSTEP = 32 / P;
     int it = 0;
-    int pending = -1;   // stage whose loads were issued in the previous iteration
     for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
-      const int s = it % kRuStages;
-      if (it >= kRuStages) mbar_wait(xempty(s), (uint32_t)((it / kRuStages) - 1) & 1u);
+      const int s = it % NX;
+      if (it >= NX) mbar_wait(xempty(s), (uint32_t)((it / NX) - 1) & 1u);
       const int b = (int)(t / a.m_tiles);
       const int m0 = (int)(t - (long long)b * a.m_tiles) * BM;
       const __nv_bfloat16* xb = a.x + (size_t)b * (size_t)a.rows_alloc * C + pn * 8;
@@ -170,20 +169,9 @@ __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel
         const bool ok = grow >= 0 && grow < a.lout;
         cp_async16(dst0 + (uint32_t)row * 16u, ok ? (const void*)(xb + (size_t)grow * C) : (const void*)a.x, ok ? 16u : 0u);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (pending >= 0) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(xfull(pending));
-      }
-      pending = s;
-    }
-    if (pending >= 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(xfull(pending));
+      // every lane's arrival fires when its copies have landed (count 32, no producer-side wait): the producer
+      // runs up to NX tiles ahead of the epilogue
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(xfull(s)) : "memory");
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -205,10 +193,11 @@ __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel
       };
       int it = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
-        const int g = it & 1, s = it % kRuStages;
+        const int g = it & 1, s = it % NX;
         const uint32_t n = (uint32_t)(it >> 1);
-        mbar_wait(xfull(s), (uint32_t)(it / kRuStages) & 1u);
+        mbar_wait(xfull(s), (uint32_t)(it / NX) & 1u);
         mbar_wait(acc1empty(g), (n & 1u) ^ 1u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core reads
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(g * 2 * C);
         const uint32_t xa = sX + (uint32_t)s * Cfg::XBYTES;
@@ -235,7 +224,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel
     for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
       if ((it & 1) != g) continue;
       const uint32_t n = (uint32_t)(it >> 1);
-      const int s = it % kRuStages;
+      const int s = it % NX;
       const int b = (int)(t / a.m_tiles);
       const int m0 = (int)(t - (long long)b * a.m_tiles) * BM;
       const bool valid = m0 + r < a.lout;

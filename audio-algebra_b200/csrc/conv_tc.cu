@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -511,9 +512,15 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<32>::SMEM));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<64>::SMEM));
+  AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[0], ru_fused_kernel<32>, kRuThreads, RuCfg<32>::SMEM));
   AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[1], ru_fused_kernel<64>, kRuThreads, RuCfg<64>::SMEM));
   st->fuse_ru = getenv("AA_NO_RU_FUSION") == nullptr;
+  // the C = 32 kernel is sized for two CTAs per SM (105 KB shared memory, 80 registers x 320 threads, 128 TMEM columns each);
+  // the persistent tile loop is correct for any grid, so a conservative occupancy answer only costs a second wave
+  st->ru_ctas_per_sm[0] = std::max(st->ru_ctas_per_sm[0], getenv("AA_RU_CTAS32") ? atoi(getenv("AA_RU_CTAS32")) : 2);
+  if (getenv("AA_DEBUG")) fprintf(stderr, "[aa] ru_fused CTAs/SM: C=32 -> %d, C=64 -> %d\n", st->ru_ctas_per_sm[0], st->ru_ctas_per_sm[1]);
   *out = st;
   return AA_OK;
 }
