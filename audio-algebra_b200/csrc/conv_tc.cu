@@ -14,6 +14,7 @@
 // kernel fuses the fader-scaled stem sum, the conv, ELU and the fp32 [B][2][N] -> bf16 [B][N][32] layout change.
 #include "aa_common.cuh"
 #include "encoder.cuh"
+#include "packed_f32x2.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -412,6 +413,77 @@ __global__ void __launch_bounds__(256) conv_l0_kernel(const L0Args a) {
   }
 }
 
+// Layer 0, common shape (cout = 32, k = 7, stride 1, 'same' padding): 2 positions per thread, all 32 output channels in
+// packed fp32x2 accumulators (channel pairs); weights are read as broadcast float4 (4 channels of one (cin, tap)), so one
+// LDS.128 feeds 4 FFMA2 -- the kernel is FMA-pipe bound (448 FMA per position) instead of shared-memory bound.
+constexpr int kL0Pos = 512;                                   // positions per CTA
+constexpr int kL0Smem = 4 * (kL0Pos + 8) * 4 + 4 * 7 * 32 * 4 + 32 * 4 + kL0Pos * 80;
+__global__ void __launch_bounds__(256, 2) conv_l0_c32k7_kernel(const L0Args a) {
+  extern __shared__ __align__(16) unsigned char l0smem[];
+  float* Xs = reinterpret_cast<float*>(l0smem);                              // [cin][kL0Pos + 8]
+  float4* Ws4 = reinterpret_cast<float4*>(Xs + 4 * (kL0Pos + 8));            // [(c*7 + j)][8] float4 = channels 4q..4q+3
+  float* Bs = reinterpret_cast<float*>(Ws4 + 4 * 7 * 8);
+  unsigned char* Os = reinterpret_cast<unsigned char*>(Bs + 32);             // [kL0Pos][80 B]
+  const int b = blockIdx.y, l0 = blockIdx.x * kL0Pos, tid = threadIdx.x;
+  for (int e = tid; e < a.cin * 7 * 32; e += 256) {
+    const int co = e & 31, cj = e >> 5;                                      // cj = c*7 + j
+    reinterpret_cast<float*>(Ws4)[cj * 32 + co] = a.w[(co * a.cin + cj / 7) * 7 + cj % 7];
+  }
+  if (tid < 32) Bs[tid] = a.bias[tid];
+  constexpr int span = kL0Pos + 6;
+  for (int e = tid; e < a.cin * span; e += 256) {
+    const int c = e / span, j = e - c * span, pos = l0 - 3 + j;
+    float v = 0.f;
+    if (pos >= 0 && pos < a.n) {
+      const long long off = ((long long)b * a.cin + c) * a.n + pos;
+      v = a.fader[0] * __ldg(a.x[0] + off);
+      for (int s = 1; s < a.n_in; ++s) v = fmaf(a.fader[s], __ldg(a.x[s] + off), v);
+    }
+    Xs[c * (kL0Pos + 8) + j] = v;
+  }
+  __syncthreads();
+  float2 acc0[16], acc1[16];                                                 // positions 2 tid and 2 tid + 1
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc0[i] = acc1[i] = make_float2(Bs[2 * i], Bs[2 * i + 1]);
+  for (int c = 0; c < a.cin; ++c) {
+    float xw[8];                                                             // x[2 tid - 3 .. 2 tid + 4]
+    const float2* xp = reinterpret_cast<const float2*>(Xs + c * (kL0Pos + 8) + 2 * tid);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = xp[i]; xw[2 * i] = t.x; xw[2 * i + 1] = t.y; }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const float4* wp = Ws4 + (c * 7 + j) * 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 w = wp[q];
+        acc0[2 * q] = pfma2(make_float2(w.x, w.y), make_float2(xw[j], xw[j]), acc0[2 * q]);
+        acc0[2 * q + 1] = pfma2(make_float2(w.z, w.w), make_float2(xw[j], xw[j]), acc0[2 * q + 1]);
+        acc1[2 * q] = pfma2(make_float2(w.x, w.y), make_float2(xw[j + 1], xw[j + 1]), acc1[2 * q]);
+        acc1[2 * q + 1] = pfma2(make_float2(w.z, w.w), make_float2(xw[j + 1], xw[j + 1]), acc1[2 * q + 1]);
+      }
+    }
+  }
+  const bool ok0 = l0 + 2 * tid < a.n, ok1 = l0 + 2 * tid + 1 < a.n;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w0[4], w1[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      w0[h] = ok0 ? pack_bf16(elu2(acc0[4 * g + h])) : 0u;
+      w1[h] = ok1 ? pack_bf16(elu2(acc1[4 * g + h])) : 0u;
+    }
+    *reinterpret_cast<uint4*>(Os + (2 * tid) * 80 + g * 16) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+    *reinterpret_cast<uint4*>(Os + (2 * tid + 1) * 80 + g * 16) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+  }
+  __syncthreads();
+  uint4* o = reinterpret_cast<uint4*>(a.out + ((long long)b * a.row_stride + l0) * 32);
+#pragma unroll
+  for (int i = 0; i < kL0Pos * 4 / 256; ++i) {
+    const int idx = tid + 256 * i, rr = idx >> 2, cv = idx & 3;
+    if (l0 + rr < a.lpad) o[idx] = *reinterpret_cast<const uint4*>(Os + rr * 80 + cv * 16);
+  }
+}
+
 // W [cout][cin][k] fp32 -> W2 [cout][K_total] bf16 in chunk order: column (tap j, c) <- W[co][c % cin][c / cin + ktap_base[j]]
 struct PackArgs {
   int n_taps, cin, k, cout, k_total;
@@ -510,6 +582,7 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_l0_c32k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<32>::SMEM));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<64>::SMEM));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -587,7 +660,10 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     for (int s = 0; s < n_stems; ++s) { a.x[s] = stems_host[s]; a.fader[s] = faders_host ? faders_host[s] : 1.0f; }
     a.cin = ly.cin; a.cout = ly.cout; a.k = ly.k; a.pad = ly.pad; a.n = (int)n; a.lpad = (int)rows_padded(lout);
     a.w = w[0]; a.bias = bvec[0]; a.out = buf[0]; a.row_stride = rows_padded(lout);
-    conv_l0_kernel<<<dim3((unsigned)((a.lpad + 255) / 256), (unsigned)batch), 256, 0, stream>>>(a);
+    if (ly.cout == 32 && ly.k == 7 && ly.pad == 3)
+      conv_l0_c32k7_kernel<<<dim3((unsigned)((a.lpad + kL0Pos - 1) / kL0Pos), (unsigned)batch), 256, kL0Smem, stream>>>(a);
+    else
+      conv_l0_kernel<<<dim3((unsigned)((a.lpad + 255) / 256), (unsigned)batch), 256, 0, stream>>>(a);
     AA_LAUNCH_CHECK();
     l = lout;
   }

@@ -127,6 +127,73 @@ def cpu_reference_rate(sample_chunks, reps):
     return sample_chunks * CHUNK / SR / min(ts), cores, ts
 
 
+def measured_bf16_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 2250.0, 2250.0, "nominal dense bf16 (no MEASURED_PEAKS.json)"
+
+
+def run_extras(dev):
+    """Secondary measurements of the same hot path (BASELINE.json configs 2 variants, 3, 5) on one GPU, reported under
+    `extras` of the JSON line: STFT power / complex variants against the HBM roofline, the bf16 tcgen05 conv encoder
+    against the measured bf16 tensor peak, one data-parallel mixer training step."""
+    import torch
+    import audio_algebra_b200 as aab
+    from audio_algebra_b200.training import MixerTrainer
+    hbm, _ = measured_peaks()
+    burst, sustained, src = measured_bf16_peaks()
+    out = {}
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    x = synth(BATCH, 4321, dev)
+    for name, cls in (("stft_power", aab.MagSpectrogramAE), ("stft_complex", aab.SpectrogramAE)):
+        m = cls(n_fft=N_FFT, hop_length=HOP)
+        res = {}
+        ms = timed(lambda: res.__setitem__("o", m.encode(x)), 10)
+        nbytes = x.numel() * 4 + res["o"].numel() * res["o"].element_size()
+        out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / hbm,
+                     "audio_s_per_s": AUDIO_S_PER_STEP / (ms * 1e-3)}
+        del res
+    del x
+    # ---- conv encoder, bf16 tcgen05 path (config 5 encode sweep point): 68.17 GFLOP per 2^17-sample chunk ----
+    dvb = aab.DVAEWrapper(debug=False, compute_dtype="bf16").cuda()
+    for B in (64, 256):
+        xe = synth(B, 99, dev)
+        ms = timed(lambda: dvb.encode(xe), 5)
+        tf = B * 68.17 / ms            # GFLOP / ms = TFLOP/s
+        out[f"encoder_bf16_B{B}"] = {"ms": ms, "tflops": tf, "frac_of_bf16_burst_peak": tf / burst, "frac_of_bf16_sustained_peak": tf / sustained,
+                                     "peak_source": src, "audio_s_per_s": B * CHUNK / SR / (ms * 1e-3), "chunk_samples": CHUNK,
+                                     "note": "SoundStreamXL-style encoder restated per SURVEY.md Appendix A (random init); bf16 operands, fp32 accumulate"}
+        del xe
+    # ---- one mixer training step (config 3: 2 stems, batch 512 x 2^16 samples, bf16 encoder, fp32 projector / losses / Adam) ----
+    Bm, Nm = 512, 65536
+    torch.manual_seed(2)
+    aa = aab.AudioAlgebra(64, 64).cuda()
+    trainer = MixerTrainer(dvb.model, aa, total_steps=100)
+    g = torch.Generator(device=dev).manual_seed(7)
+    stems = [torch.rand(Bm, 2, Nm, generator=g, device=dev) - 0.5 for _ in range(2)]
+    ms = timed(lambda: trainer.step(stems, [1.4630, -0.5718]), 3, warm=1)
+    out["mixer_train_step"] = {"ms": ms, "batch": Bm, "chunk_samples": Nm, "stems": 2, "encoder_passes": 4,
+                               "audio_s_per_s": Bm * Nm / SR / (ms * 1e-3),
+                               "note": "train_aa_mixer_accel step: do_mixing (3 encodes) + batch encode, projector fwd/bwd, 4 loss terms, flat Adam"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -249,6 +316,11 @@ def run_ours(args):
                          "note": "fp32 FFT math + shared-memory exchange bound, not HBM bound (DESIGN.md)"},
             "clocks": clocks,
         }
+        if world == 1 and not args.no_extras:
+            try:
+                line["extras"] = run_extras(dev)
+            except Exception as e:   # extras never invalidate the headline line
+                line["extras"] = {"error": repr(e)}
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"32 of the {BATCH} chunks, best of 3 ({min(ts):.3f} s), oracle restatement of "
@@ -265,6 +337,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary (encoder / variants / training-step) measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -273,7 +346,7 @@ def main():
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-extras"] if args.no_extras else [])
         return subprocess.call(cmd)
     return run_ours(args)
 
