@@ -745,7 +745,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     a.out_row_stride = rows_padded(lout);
     a.elu = ly.elu; a.tanh_out = (last && apply_tanh) ? 1 : 0;
     const int stage_bytes = BM * p.bk * 2 + ((bn * p.bk * 2 + 1023) & ~1023);
-    a.n_epi = last ? 1 : (bn <= 64 ? 4 : (bn <= 128 ? 2 : 1));
+    a.n_epi = last ? 1 : (bn <= 64 ? 4 : (bn <= 128 ? 3 : 1));
     a.n_acc = std::min(kMaxAcc, std::min(512 / bn, 2 * a.n_epi));
     const int staging = a.n_epi * ((last ? 0 : BM * (bn * 2 + 16)) + bn * 4);
     a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging) / stage_bytes));
