@@ -175,3 +175,30 @@ def test_full_size_properties(aab):
     energy = ((fr * w) ** 2).sum(-1) * 2048            # [8,2,257]
     onesided = 2 * p.sum(dim=-2) - p[..., 0, :] - p[..., -1, :]
     assert rel_l2(onesided, energy) < 1e-5
+
+
+def test_mel_epilogue_variants(aab):
+    """The fused n_fft=2048 kernel has two mel epilogues: segment sums for torchaudio's triangular HTK / norm=None
+    filterbank (verified entry by entry at plan creation) and per-filter weight tables for anything else.  Both against
+    the float64 product power @ fb, on inputs with a large dynamic range across bins."""
+    import os
+    O = _oracle()
+    g = torch.Generator().manual_seed(77)
+    t = torch.arange(16384) / 48000.0
+    x = 0.8 * torch.sin(2 * np.pi * 440.0 * t)[None, None] + 1e-3 * (torch.rand(3, 2, 16384, generator=g) - 0.5)
+    p = O.power_spectrogram(x, 2048, 512)                                         # float64 [3,2,1025,T]
+    for kw in (dict(), dict(norm="slaney"), dict(mel_scale="slaney"), dict(n_mels=80, f_min=30.0, f_max=16000.0)):
+        m = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512, **kw)
+        ref = torch.einsum("bcft,fm->bcmt", p, m.fb.double())
+        assert rel_l2(m.encode(x.cuda()), ref) < TOL, kw
+        # per-filter check (a global norm would hide a wrong quiet filter next to the 440 Hz peak)
+        got = m.encode(x.cuda()).cpu().double()
+        err = (got - ref).abs().amax(dim=(0, 1, 3)) / ref.abs().amax(dim=(0, 1, 3)).clamp_min(1e-30)
+        assert err.max().item() < 1e-4, (kw, err.argmax().item(), err.max().item())
+    os.environ["AA_MEL_GENERAL"] = "1"      # read at plan creation: force the weight-table epilogue for the default bank
+    try:
+        m = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512)
+        ref = torch.einsum("bcft,fm->bcmt", p, m.fb.double())
+        assert rel_l2(m.encode(x.cuda()), ref) < TOL
+    finally:
+        os.environ.pop("AA_MEL_GENERAL", None)
