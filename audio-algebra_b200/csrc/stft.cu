@@ -28,7 +28,6 @@
 
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -58,7 +57,6 @@ struct StftArgs {
   const int4* mel_steps;  // fast path: [kWarps][mel_steps_per_warp + 1][4] step headers, then the step weights
   int mel_steps_per_warp, mel_hdr_bytes, mel_w_bytes;
   const float* lane_consts;  // fast path: float4[32] Hann phases + float2[32] W_2048^lane
-  int mel_tri;               // fast path: 1 = triangular filterbank -> segment-sum epilogue (tables in mel_steps)
 };
 
 __device__ __forceinline__ float fetch_sample(const float* __restrict__ p, long long i, long long n_in,
@@ -90,11 +88,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ int4 lds_i4(uint32_t addr) {
@@ -450,53 +443,6 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
         // 6 different P lines (skewed by 16 B) -> conflict-free; step headers and weights (one float4 per 4
         // bins, zero-padded to the longest filter of the step) live in shared memory; accumulators are
         // packed (rowA,rowB) FFMA2.
-        if (a.mel_tri) {
-          // ---- triangular filterbank: segment sums.  The filter edges f_0 < f_1 < ... cut the bins into segments; on
-          // segment s the rising weight of filter s is u(k) = a_s + j b_s (j = bin index inside the segment) and the
-          // falling weight of filter s-1 is 1 - u(k), so with S = sum P and T = sum (j+1) P:
-          //     U_s = sum u P = (a-b) S + b T,   D_s = sum (1-u) P = S - U_s,   mel[m] = U_m + D_{m+1}.
-          // A lane group (6 lanes = the tile's frames) walks ONE segment from its top bin down with a running suffix
-          // sum R (S = final R, T = sum of the R's): every P value is read once, there are no weight loads, and
-          // 5 groups = 5 consecutive segments give 4 filters per step (D of the next segment arrives by shuffle).
-          const int g = lane / kWarps, fl = lane - g * kWarps;     // lanes 30, 31: g = 5 (idle)
-          const bool gactive = g < 5;
-          unsigned plane_sz = (unsigned)a.n_mels * (unsigned)a.n_frames;
-          unsigned n_frames_u = (unsigned)a.n_frames;
-          float* outA = a.out + (size_t)rowA * plane_sz + (f0 + fl);
-          unsigned flags = ((gactive && (f0 + fl < a.n_frames)) ? 1u : 0u) | ((rowA + 1 < a.rows) ? 2u : 0u);
-          unsigned pbase = smem_u32(P + (gactive ? fl : 0) * kPLine);
-          unsigned hp = smem_u32(s_melh + warp * (a.mel_steps_per_warp + 1) * 8);   // [warp][step][8] int4: 5 groups, step info
-          unsigned gofs = (unsigned)(gactive ? g : 0) * 16u;
-          asm volatile("" : "+r"(plane_sz), "+r"(n_frames_u), "+l"(outA), "+r"(flags), "+r"(pbase), "+r"(hp), "+r"(gofs));
-          int4 hs = lds_i4(hp + 5 * 16);          // {n_max (even), first filter, filters in this step, 0}
-          int4 h = lds_i4(hp + gofs);             // {byte offset of the segment's top bin, bins, c1 = (a-b)/4, c2 = b/4}
-#pragma unroll 1
-          while (hs.x != 0) {
-            hp += 128;
-            const int4 hsn = lds_i4(hp + 5 * 16), hn = lds_i4(hp + gofs);
-            unsigned addr = pbase + (unsigned)h.x;
-            const int n = gactive ? h.y : 0;
-            float2 R = make_float2(0.f, 0.f), T = R;
-            float2 p0 = lds_f2(addr), p1 = lds_f2(addr - 8);
-#pragma unroll 1
-            for (int i = 0; i < hs.x; i += 2) {
-              addr -= 16;
-              const float2 q0 = lds_f2(addr), q1 = lds_f2(addr - 8);   // reads below the segment stay inside shared memory
-              if (i < n) { R = padd(R, p0); T = padd(T, R); }
-              if (i + 1 < n) { R = padd(R, p1); T = padd(T, R); }
-              p0 = q0; p1 = q1;
-            }
-            const float2 U = pfma(T, __int_as_float(h.w), pmuls(R, __int_as_float(h.z)));
-            const float2 D = psub(pmuls(R, 0.25f), U);
-            const float dnx = __shfl_down_sync(0xffffffffu, D.x, kWarps), dny = __shfl_down_sync(0xffffffffu, D.y, kWarps);
-            if ((flags & 1u) && g < hs.z) {
-              float* o = outA + (unsigned)(hs.y + g) * n_frames_u;
-              asm volatile("st.global.f32 [%0], %1;" ::"l"(o), "f"(U.x + dnx) : "memory");
-              if (flags & 2u) asm volatile("st.global.f32 [%0], %1;" ::"l"(o + plane_sz), "f"(U.y + dny) : "memory");
-            }
-            hs = hsn; h = hn;
-          }
-        } else {
         const int q = lane >> 3, fl = lane & 7;
         const bool factive = fl < kWarps;
         // 32-bit output indexing (the host routes outputs of >= 2^31 elements to the generic kernel)
@@ -548,7 +494,6 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
           }
           h = hn;
         }
-        }   // general (weight-table) mel epilogue
       } else {  // MODE_POWER: lanes = (32 bins) x (6 frames) -> 24-byte runs along the frame axis
         const int fsub = tid % kWarps, ksub = tid / kWarps;
         const int fr = f0 + fsub;
@@ -682,8 +627,6 @@ struct AaStftPlan {
   float* d_lane_consts = nullptr;
   int mel_steps_per_warp = 0, mel_hdr_bytes = 0, mel_w_bytes = 0;
   int fast_smem = 0, fast_grid_per_sm = 2;
-  int4* d_mel_tri = nullptr;     // fast path, triangular filterbank: segment tables of the segment-sum epilogue
-  int mel_tri = 0, mel_tri_spw = 0, mel_tri_bytes = 0, fast_smem_tri = 0;
   // resources of aa_stft_mel_f32_host (created lazily)
   cudaStream_t hstream[2] = {nullptr, nullptr};
   float* hbuf_in[2] = {nullptr, nullptr};
@@ -856,100 +799,9 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
                          cudaMemcpyHostToDevice));
     }
   }
-  if (p->fast && n_mels > 0 && getenv("AA_MEL_GENERAL") == nullptr) {
-    // Is the filterbank the (HTK, norm=None) triangular one of torchaudio.functional.melscale_fbanks?  Then filter m rises
-    // linearly on segment [f_m, f_{m+1}) and falls on [f_{m+1}, f_{m+2}), and the fused epilogue can use segment sums
-    // (see the kernel).  Verified against the caller's matrix entry by entry; anything else keeps the weight tables.
-    const int F = p->n_freq;
-    const double nyq = (double)((long long)sample_rate / 2), df = nyq / (double)(F - 1);
-    bool tri = sample_rate > 0 && f_max > f_min;
-    std::vector<double> f_pts(n_mels + 2);
-    std::vector<int> k0(n_mels + 2, F);
-    if (tri) {
-      const double m_min = hz_to_mel_htk(f_min), m_max = hz_to_mel_htk(f_max);
-      for (int i = 0; i < n_mels + 2; ++i)
-        f_pts[i] = 700.0 * (std::pow(10.0, (m_min + (m_max - m_min) * (double)i / (double)(n_mels + 1)) / 2595.0) - 1.0);
-      for (int i = 0; i < n_mels + 2; ++i) {          // first bin at or above f_i
-        long long k = (long long)std::ceil(f_pts[i] / df - 1e-9);
-        k0[i] = (int)std::min<long long>(std::max<long long>(k, 0), F);
-      }
-      for (int i = 0; i + 1 < n_mels + 2; ++i) tri = tri && f_pts[i + 1] > f_pts[i] && k0[i + 1] >= k0[i];
-    }
-    std::vector<float> c1(n_mels + 1, 0.f), c2(n_mels + 1, 0.f);
-    if (tri) {
-      std::vector<float> wchk((size_t)F * n_mels, 0.f);
-      for (int sgm = 0; sgm <= n_mels; ++sgm) {
-        const double delta = f_pts[sgm + 1] - f_pts[sgm];
-        const double av = ((double)k0[sgm] * df - f_pts[sgm]) / delta, bv = df / delta;
-        c1[sgm] = (float)(0.25 * (av - bv));
-        c2[sgm] = (float)(0.25 * bv);
-        for (int k = k0[sgm]; k < k0[sgm + 1]; ++k) {
-          const double u = av + (double)(k - k0[sgm]) * bv;
-          if (sgm < n_mels) wchk[(size_t)k * n_mels + sgm] += (float)u;
-          if (sgm >= 1) wchk[(size_t)k * n_mels + sgm - 1] += (float)(1.0 - u);
-        }
-      }
-      // the caller's matrix (or the one generated above from the same formula) must agree everywhere
-      std::vector<float> fbm((size_t)F * n_mels);
-      if (fb_host) std::copy(fb_host, fb_host + (size_t)F * n_mels, fbm.begin());
-      else {
-        for (int k = 0; k < F; ++k)
-          for (int m = 0; m < n_mels; ++m) {
-            const double f = nyq * (double)k / (double)(F - 1);
-            const double down = (f - f_pts[m]) / (f_pts[m + 1] - f_pts[m]), up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
-            fbm[(size_t)k * n_mels + m] = (float)std::max(0.0, std::min(down, up));
-          }
-      }
-      for (size_t i = 0; i < fbm.size() && tri; ++i) tri = std::fabs(fbm[i] - wchk[i]) <= 4e-6f;
-    }
-    if (tri) {
-      struct TStep { int4 g[8]; };
-      std::vector<TStep> steps;
-      for (int m0 = 0; m0 < n_mels; m0 += 4) {
-        TStep st;
-        for (int i = 0; i < 8; ++i) st.g[i] = make_int4(0, 0, 0, 0);
-        int nmax = 0;
-        for (int gg = 0; gg < 5; ++gg) {
-          const int sgm = m0 + gg;
-          if (sgm > n_mels) continue;
-          const int n = k0[sgm + 1] - k0[sgm];
-          nmax = std::max(nmax, n);
-          int ci1, ci2;
-          std::memcpy(&ci1, &c1[sgm], 4);
-          std::memcpy(&ci2, &c2[sgm], 4);
-          st.g[gg] = make_int4(n > 0 ? (k0[sgm] + n - 1) * 8 : 0, n, ci1, ci2);
-        }
-        nmax = std::max(2, (nmax + 1) & ~1);
-        st.g[5] = make_int4(nmax, m0, std::min(4, n_mels - m0), 0);
-        steps.push_back(st);
-      }
-      std::vector<int> order(steps.size()), load(kWarps, 0);
-      for (size_t i = 0; i < steps.size(); ++i) order[i] = (int)i;
-      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return steps[x].g[5].x > steps[y].g[5].x; });
-      std::vector<std::vector<int>> per_warp(kWarps);
-      for (int i : order) {
-        int best = 0;
-        for (int wq = 1; wq < kWarps; ++wq) if (load[wq] < load[best]) best = wq;
-        per_warp[best].push_back(i);
-        load[best] += steps[i].g[5].x * 3 + 24;
-      }
-      size_t spw = 1;
-      for (auto& l : per_warp) spw = std::max(spw, l.size());
-      std::vector<int4> tab((size_t)kWarps * (spw + 1) * 8, make_int4(0, 0, 0, 0));   // a zero step (n_max = 0) ends a warp's list
-      for (int wq = 0; wq < kWarps; ++wq)
-        for (size_t i = 0; i < per_warp[wq].size(); ++i)
-          for (int gg = 0; gg < 8; ++gg) tab[((size_t)wq * (spw + 1) + i) * 8 + gg] = steps[per_warp[wq][i]].g[gg];
-      p->mel_tri = 1;
-      p->mel_tri_spw = (int)spw;
-      p->mel_tri_bytes = (int)(sizeof(int4) * tab.size());
-      AA_CUDA(cudaMalloc(&p->d_mel_tri, p->mel_tri_bytes));
-      AA_CUDA(cudaMemcpy(p->d_mel_tri, tab.data(), p->mel_tri_bytes, cudaMemcpyHostToDevice));
-    }
-  }
   if (p->fast) {
     const int smem = ((kWarps - 1) * hop + 2048) * 8 + kStageBytes + kTableBytes + p->mel_hdr_bytes + p->mel_w_bytes + 32;
     p->fast_smem = smem;
-    p->fast_smem_tri = ((kWarps - 1) * hop + 2048) * 8 + kStageBytes + kTableBytes + p->mel_tri_bytes + 32;
     AA_CUDA(cudaFuncSetAttribute(stft2048_kernel<MODE_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     AA_CUDA(cudaFuncSetAttribute(stft2048_kernel<MODE_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     AA_CUDA(cudaFuncSetAttribute(stft2048_kernel<MODE_MEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -968,7 +820,7 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
 
 int aa_stft_plan_destroy(AaStftPlan* p) {
   if (!p) return AA_OK;
-  cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4); cudaFree(p->d_mel_steps); cudaFree(p->d_lane_consts); cudaFree(p->d_mel_tri);
+  cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4); cudaFree(p->d_mel_steps); cudaFree(p->d_lane_consts);
   for (int i = 0; i < 2; ++i) {
     if (p->hbuf_in[i]) cudaFree(p->hbuf_in[i]);
     if (p->hbuf_out[i]) cudaFree(p->hbuf_out[i]);
@@ -1023,19 +875,15 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
     a.n_tiles = pairs * a.tiles_per_pair;
     a.mel_steps = p->d_mel_steps; a.mel_steps_per_warp = p->mel_steps_per_warp;
     a.mel_hdr_bytes = p->mel_hdr_bytes; a.mel_w_bytes = p->mel_w_bytes; a.lane_consts = p->d_lane_consts;
-    a.mel_tri = 0;
-    if (mode == MODE_MEL && p->mel_tri) {
-      a.mel_tri = 1; a.mel_steps = p->d_mel_tri; a.mel_steps_per_warp = p->mel_tri_spw; a.mel_hdr_bytes = p->mel_tri_bytes; a.mel_w_bytes = 0;
-    }
     AA_REQUIRE(a.n_tiles < (1LL << 31) && rows < (1LL << 30) && n_pad < (1LL << 30), "problem too large for the fast STFT path");
     const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)p->fast_grid_per_sm * aa::num_sms());
-    const int smem = a.mel_tri ? p->fast_smem_tri : p->fast_smem;
+    const int smem = p->fast_smem;
     if (mode == MODE_COMPLEX) stft2048_kernel<MODE_COMPLEX><<<(unsigned)grid, kThreads, smem, st>>>(a);
     else if (mode == MODE_POWER) stft2048_kernel<MODE_POWER><<<(unsigned)grid, kThreads, smem, st>>>(a);
     else stft2048_kernel<MODE_MEL><<<(unsigned)grid, kThreads, smem, st>>>(a);
   } else {
     a.tiles_per_pair = 0; a.n_tiles = 0; a.mel_steps = nullptr; a.mel_steps_per_warp = 0;
-    a.mel_hdr_bytes = a.mel_w_bytes = 0; a.lane_consts = nullptr; a.mel_tri = 0;
+    a.mel_hdr_bytes = a.mel_w_bytes = 0; a.lane_consts = nullptr;
     const int64_t grid = rows * n_frames;
     AA_REQUIRE(grid < (1LL << 31), "grid too large (%lld frames)", (long long)grid);
     const int M = p->n_fft / 2, smem = M * 12 + 64;
