@@ -12,14 +12,13 @@
 // advanced by j*d rows: every x tile (128 + 6 d rows) is loaded once for all 7 taps.  The k7 and k1 weights stay
 // resident in shared memory for the whole (persistent) kernel.
 //
-// Warp roles (320 threads): warp 0 = x-tile producer (16-byte cp.async straight into the panel layout, zero fill =
+// Warp roles (64 + 128 NG threads): warp 0 = x-tile producer (16-byte cp.async straight into the panel layout, zero fill =
 // conv padding), warp 1 = tcgen05.mma issuer (k7 of tile i+1 is issued before k1 of tile i: the tensor pipe works
-// while the epilogue turns tile i's first accumulator into the k1 operand), warps 2..9 = two epilogue groups that
-// alternate tiles: TMEM -> +b7 -> ELU -> bf16 panel tile (the k1 A operand) ; TMEM -> +b1 + x (from the resident x
+// while the epilogue turns earlier tiles' first accumulators into k1 operands), warps 2.. = NG epilogue groups that
+// take tiles round-robin: TMEM -> +b7 -> ELU -> bf16 panel tile (the k1 A operand) ; TMEM -> +b1 + x (from the resident x
 // tile) -> ELU -> bf16 -> staged -> coalesced 16-byte stores.
 #pragma once
 
-constexpr int kRuThreads = 64 + 256;
 
 struct RuArgs {
   const __nv_bfloat16* x;    // [B][rows_alloc][C] channels-last
@@ -48,10 +47,16 @@ struct RuCfg {
   static constexpr int OFF_W7 = 1024;
   static constexpr int OFF_W1 = OFF_W7 + W7BYTES;
   static constexpr int OFF_X = OFF_W1 + W1BYTES;
-  static constexpr int NX = (C == 64) ? 4 : 6;           // x tiles in flight
+  static constexpr int NG = 2;                           // epilogue groups (4 warps each); C = 32 runs two CTAs per SM instead
+  static constexpr int THREADS = 64 + 128 * NG;
+  static constexpr int NX = (C == 64) ? 4 : 6;           // x tiles in flight (> NG: a stage is held until its tile's phase 2 has read the residual)
+  // the 1x1 conv of tile i is issued after the k7 conv of tile i + LAG; LAG <= NX - 1, otherwise the x stage that tile
+  // i + LAG needs would only be released by a phase 2 that waits for that very 1x1 conv
+  static constexpr int LAG = (NG - 1 < NX - 1) ? NG - 1 : NX - 1;
   static constexpr int OFF_T = OFF_X + NX * XBYTES;
-  static constexpr int SMEM = OFF_T + 2 * TBYTES + 128;  // + alignment slack
-  static constexpr int TMEM_COLS = 4 * C;                // {acc1, acc2} x 2 epilogue groups
+  static constexpr int SMEM = OFF_T + NG * TBYTES + 128; // + alignment slack
+  static constexpr int TMEM_USED = 2 * C * NG;           // {acc1, acc2} per epilogue group
+  static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;   // power of two
 };
 
 // K-major, no-swizzle shared-memory matrix descriptor: 8-row groups 128 B apart (SBO), K core matrices `lbo` bytes apart
@@ -89,31 +94,33 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t w) {
 // named barrier of one epilogue group (immediate ids: a register id would reserve all 16 hardware barriers)
 __device__ __forceinline__ void group_sync(int g) {
   if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-  else asm volatile("bar.sync 2, 128;" ::: "memory");
+  else if (g == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+  else if (g == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
+  else asm volatile("bar.sync 4, 128;" ::: "memory");
 }
 
 template <int C>
-__global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel(const RuArgs a) {
+__global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused_kernel(const RuArgs a) {
   using Cfg = RuCfg<C>;
-  constexpr int P = Cfg::P, NX = Cfg::NX;
+  constexpr int P = Cfg::P, NX = Cfg::NX, NG = Cfg::NG, LAG = Cfg::LAG, kRuThreads = Cfg::THREADS;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
-  // barriers: xfull[NX] xempty[NX] acc1full[2] acc1empty[2] tfull[2] acc2full[2] acc2empty[2], tmem slot
+  // barriers: xfull[NX] xempty[NX] acc1full[NG] acc1empty[NG] tfull[NG] acc2full[NG] acc2empty[NG], tmem slot
   auto xfull = [&](int s) { return base + 8u * s; };
   auto xempty = [&](int s) { return base + 8u * (NX + s); };
   auto acc1full = [&](int g) { return base + 8u * (2 * NX + g); };
-  auto acc1empty = [&](int g) { return base + 8u * (2 * NX + 2 + g); };
-  auto tfull = [&](int g) { return base + 8u * (2 * NX + 4 + g); };
-  auto acc2full = [&](int g) { return base + 8u * (2 * NX + 6 + g); };
-  auto acc2empty = [&](int g) { return base + 8u * (2 * NX + 8 + g); };
-  const uint32_t tmem_slot = base + 8u * (2 * NX + 10);
+  auto acc1empty = [&](int g) { return base + 8u * (2 * NX + NG + g); };
+  auto tfull = [&](int g) { return base + 8u * (2 * NX + 2 * NG + g); };
+  auto acc2full = [&](int g) { return base + 8u * (2 * NX + 3 * NG + g); };
+  auto acc2empty = [&](int g) { return base + 8u * (2 * NX + 4 * NG + g); };
+  const uint32_t tmem_slot = base + 8u * (2 * NX + 5 * NG);
   const uint32_t sbias = base + Cfg::OFF_BIAS;   // b7[C], b1[C]
   const uint32_t sW7 = base + Cfg::OFF_W7, sW1 = base + Cfg::OFF_W1, sX = base + Cfg::OFF_X, sT = base + Cfg::OFF_T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NX; ++s) { mbar_init(xfull(s), 32); mbar_init(xempty(s), 4); }
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < NG; ++g) {
       mbar_init(acc1full(g), 1); mbar_init(acc1empty(g), 4); mbar_init(tfull(g), 4);
       mbar_init(acc2full(g), 1); mbar_init(acc2empty(g), 4);
     }
@@ -178,8 +185,8 @@ __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       auto issue_k1 = [&](int j) {
-        const int g = j & 1;
-        const uint32_t n = (uint32_t)(j >> 1);
+        const int g = j % NG;
+        const uint32_t n = (uint32_t)(j / NG);
         mbar_wait(tfull(g), n & 1u);
         mbar_wait(acc2empty(g), (n & 1u) ^ 1u);
         tc_fence_after();
@@ -193,8 +200,8 @@ __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel
       };
       int it = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
-        const int g = it & 1, s = it % NX;
-        const uint32_t n = (uint32_t)(it >> 1);
+        const int g = it % NG, s = it % NX;
+        const uint32_t n = (uint32_t)(it / NG);
         mbar_wait(xfull(s), (uint32_t)(it / NX) & 1u);
         mbar_wait(acc1empty(g), (n & 1u) ^ 1u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core reads
@@ -209,12 +216,12 @@ __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel
                       make_desc_ns(sW7 + (uint32_t)(j * P + 2 * kk) * Cfg::WS, Cfg::WS), idesc, (j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(acc1full(g));
-        if (it >= 1) issue_k1(it - 1);
+        if (it >= LAG) issue_k1(it - LAG);   // the oldest tile still waiting for its 1x1 conv: its operand is (nearly) ready by now
       }
-      if (it >= 1) issue_k1(it - 1);
+      for (int j = (it >= LAG ? it - LAG : 0); j < it; ++j) issue_k1(j);
     }
   } else {
-    // ===================== epilogue: group g = tiles with (it & 1) == g; thread = one row of the tile =====================
+    // ===================== epilogue: group g = tiles with it % NG == g; thread = one row of the tile =====================
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
     const int g = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;          // row in the tile
@@ -222,8 +229,8 @@ __global__ void __launch_bounds__(kRuThreads, (C == 32) ? 2 : 1) ru_fused_kernel
     const uint32_t tg = sT + (uint32_t)g * Cfg::TBYTES;
     int it = 0;
     for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
-      if ((it & 1) != g) continue;
-      const uint32_t n = (uint32_t)(it >> 1);
+      if (it % NG != g) continue;
+      const uint32_t n = (uint32_t)(it / NG);
       const int s = it % NX;
       const int b = (int)(t / a.m_tiles);
       const int m0 = (int)(t - (long long)b * a.m_tiles) * BM;

@@ -587,8 +587,8 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<64>::SMEM));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[0], ru_fused_kernel<32>, kRuThreads, RuCfg<32>::SMEM));
-  AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[1], ru_fused_kernel<64>, kRuThreads, RuCfg<64>::SMEM));
+  AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[0], ru_fused_kernel<32>, RuCfg<32>::THREADS, RuCfg<32>::SMEM));
+  AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[1], ru_fused_kernel<64>, RuCfg<64>::THREADS, RuCfg<64>::SMEM));
   st->fuse_ru = getenv("AA_NO_RU_FUSION") == nullptr;
   // the C = 32 kernel is sized for two CTAs per SM (105 KB shared memory, 80 registers x 320 threads, 128 TMEM columns each);
   // the persistent tile loop is correct for any grid, so a conservative occupancy answer only costs a second wave
@@ -688,10 +688,10 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
       ra.rows_alloc = rows_padded(l); ra.tiles = batch * ra.m_tiles;
       if (ly.cin == 32) {
         const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms() * st->ru_ctas_per_sm[0]);
-        ru_fused_kernel<32><<<grid, kRuThreads, RuCfg<32>::SMEM, stream>>>(ra);
+        ru_fused_kernel<32><<<grid, RuCfg<32>::THREADS, RuCfg<32>::SMEM, stream>>>(ra);
       } else {
         const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms() * st->ru_ctas_per_sm[1]);
-        ru_fused_kernel<64><<<grid, kRuThreads, RuCfg<64>::SMEM, stream>>>(ra);
+        ru_fused_kernel<64><<<grid, RuCfg<64>::THREADS, RuCfg<64>::SMEM, stream>>>(ra);
       }
       AA_LAUNCH_CHECK();
       cur = dst;
