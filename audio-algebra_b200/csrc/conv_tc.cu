@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(256) conv_l0_kernel(const L0Args a) {
 // packed fp32x2 accumulators (channel pairs); weights are read as broadcast float4 (4 channels of one (cin, tap)), so one
 // LDS.128 feeds 4 FFMA2 -- the kernel is FMA-pipe bound (448 FMA per position) instead of shared-memory bound.
 constexpr int kL0Pos = 512;                                   // positions per CTA
-constexpr int kL0Smem = 4 * (kL0Pos + 8) * 4 + 4 * 7 * 32 * 4 + 32 * 4 + kL0Pos * 80;
+constexpr int kL0Smem = 4 * (kL0Pos + 8) * 4 + 4 * 7 * 32 * 4 + 32 * 4 + kL0Pos * 80;   // (also covers 2 buffers x CIN <= 2 of the register kernel)
 __global__ void __launch_bounds__(256, 2) conv_l0_c32k7_kernel(const L0Args a) {
   extern __shared__ __align__(16) unsigned char l0smem[];
   float* Xs = reinterpret_cast<float*>(l0smem);                              // [cin][kL0Pos + 8]
@@ -481,6 +481,117 @@ __global__ void __launch_bounds__(256, 2) conv_l0_c32k7_kernel(const L0Args a) {
   for (int i = 0; i < kL0Pos * 4 / 256; ++i) {
     const int idx = tid + 256 * i, rr = idx >> 2, cv = idx & 3;
     if (l0 + rr < a.lpad) o[idx] = *reinterpret_cast<const uint4*>(Os + rr * 80 + cv * 16);
+  }
+}
+
+// Layer 0, stereo / mono input (CIN <= 2, cout = 32, k = 7): a thread owns 4 output channels (its 4 x CIN x 7 weights stay in
+// registers) and a strip of 16 consecutive positions (the 22-sample input window per channel stays in registers too), so the
+// inner loop is pure packed FFMA2: 28 x CIN per position and thread.  Lanes = 8 channel groups x 4 strips; a block of 256
+// threads covers 512 positions.  Shared memory is touched for 14 x CIN weight float4s + 11 x CIN input float2s per thread and
+// block (broadcast reads) and for the bf16 output staging.
+template <int CIN>
+__global__ void __launch_bounds__(256, 2) conv_l0_reg_kernel(const L0Args a, int tiles_per_row, int n_tiles) {
+  extern __shared__ __align__(16) unsigned char l0smem[];
+  float* Xs = reinterpret_cast<float*>(l0smem);                              // 2 buffers x [CIN][kL0Pos + 8], index 0 = position l0 - 3
+  float4* Ws4 = reinterpret_cast<float4*>(Xs + 2 * CIN * (kL0Pos + 8));      // [(c*7 + j)][8] float4 = channels 4q..4q+3
+  float* Bs = reinterpret_cast<float*>(Ws4 + CIN * 7 * 8);
+  unsigned char* Os = reinterpret_cast<unsigned char*>(Bs + 32);             // [kL0Pos][80 B]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < CIN * 7 * 32; e += 256) {
+    const int co = e & 31, cj = e >> 5;                                      // cj = c*7 + j
+    reinterpret_cast<float*>(Ws4)[cj * 32 + co] = a.w[(co * CIN + cj / 7) * 7 + cj % 7];
+  }
+  if (tid < 32) Bs[tid] = a.bias[tid];
+  constexpr int span = kL0Pos + 6;
+  constexpr int NLD = (CIN * span + 255) / 256;                              // input samples per thread and tile
+  // element e of tile t: offset into a stem tensor, or -1 outside the signal (zero = conv padding) / past the last tile
+  auto elem_off = [&](int t, int e) -> long long {
+    if (t >= n_tiles || e >= CIN * span) return -1;
+    const int b = t / tiles_per_row, l0 = (t - b * tiles_per_row) * kL0Pos;
+    const int c = e / span, pos = l0 - 3 + (e - c * span);
+    if (pos < 0 || pos >= a.n) return -1;
+    return ((long long)b * CIN + c) * a.n + pos;
+  };
+  // the raw samples of the first two stems are loaded early (in flight during the FMAs of the current tile); the fader
+  // scaling and the stem sum (aa_mixer.py:303,309) are applied when they are parked in shared memory
+  auto load_raw = [&](int t, int e, float& r0, float& r1) {
+    const long long off = elem_off(t, e);
+    r0 = r1 = 0.f;
+    if (off >= 0) {
+      r0 = __ldg(a.x[0] + off);
+      if (a.n_in > 1) r1 = __ldg(a.x[1] + off);
+    }
+  };
+  auto stash = [&](float* X, int t, int e, float r0, float r1) {
+    if (e < CIN * span) {
+      float v = a.fader[0] * r0;
+      if (a.n_in > 1) v = fmaf(a.fader[1], r1, v);
+      if (a.n_in > 2) {
+        const long long off = elem_off(t, e);
+        if (off >= 0)
+          for (int s2 = 2; s2 < a.n_in; ++s2) v = fmaf(a.fader[s2], __ldg(a.x[s2] + off), v);
+      }
+      const int c = e / span;
+      X[c * (kL0Pos + 8) + (e - c * span)] = v;
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    float r0, r1;
+    load_raw(blockIdx.x, tid + 256 * i, r0, r1);
+    stash(Xs, blockIdx.x, tid + 256 * i, r0, r1);
+  }
+  __syncthreads();
+  const int lane = tid & 31, cg = lane & 7, strip = (tid >> 5) * 4 + (lane >> 3);   // strip: positions 16 strip .. +15
+  float2 w01[CIN * 7], w23[CIN * 7];                                        // channel pairs (4cg, 4cg+1), (4cg+2, 4cg+3)
+#pragma unroll
+  for (int cj = 0; cj < CIN * 7; ++cj) {
+    const float4 w = Ws4[cj * 8 + cg];
+    w01[cj] = make_float2(w.x, w.y);
+    w23[cj] = make_float2(w.z, w.w);
+  }
+  const float2 b01 = make_float2(Bs[4 * cg], Bs[4 * cg + 1]), b23 = make_float2(Bs[4 * cg + 2], Bs[4 * cg + 3]);
+  int buf = 0;
+#pragma unroll 1
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    const int b = t / tiles_per_row, l0 = (t - b * tiles_per_row) * kL0Pos;
+    float nxt0[NLD], nxt1[NLD];                                             // next tile's raw inputs: in flight during the FMAs below
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) load_raw(t + gridDim.x, tid + 256 * i, nxt0[i], nxt1[i]);
+    const float* X = Xs + buf * CIN * (kL0Pos + 8);
+    float xw[CIN][22];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float2* xp = reinterpret_cast<const float2*>(X + c * (kL0Pos + 8) + 16 * strip);
+#pragma unroll
+      for (int i = 0; i < 11; ++i) { const float2 v = xp[i]; xw[c][2 * i] = v.x; xw[c][2 * i + 1] = v.y; }
+    }
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      float2 a01 = b01, a23 = b23;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const float2 xx = make_float2(xw[c][p + j], xw[c][p + j]);
+          a01 = pfma2(w01[c * 7 + j], xx, a01);
+          a23 = pfma2(w23[c * 7 + j], xx, a23);
+        }
+      const bool ok = l0 + 16 * strip + p < a.n;
+      const uint32_t o0 = ok ? pack_bf16(elu2(a01)) : 0u, o1 = ok ? pack_bf16(elu2(a23)) : 0u;
+      *reinterpret_cast<uint2*>(Os + (16 * strip + p) * 80 + cg * 8) = make_uint2(o0, o1);
+    }
+    __syncthreads();
+    uint4* o = reinterpret_cast<uint4*>(a.out + ((long long)b * a.row_stride + l0) * 32);
+#pragma unroll
+    for (int i = 0; i < kL0Pos * 4 / 256; ++i) {
+      const int idx = tid + 256 * i, rr = idx >> 2, cv = idx & 3;
+      if (l0 + rr < a.lpad) o[idx] = *reinterpret_cast<const uint4*>(Os + rr * 80 + cv * 16);
+    }
+    float* Xn = Xs + (buf ^ 1) * CIN * (kL0Pos + 8);
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) stash(Xn, t + gridDim.x, tid + 256 * i, nxt0[i], nxt1[i]);
+    __syncthreads();
   }
 }
 
@@ -583,6 +694,8 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_c32k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<32>::SMEM));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<64>::SMEM));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -660,7 +773,14 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     for (int s = 0; s < n_stems; ++s) { a.x[s] = stems_host[s]; a.fader[s] = faders_host ? faders_host[s] : 1.0f; }
     a.cin = ly.cin; a.cout = ly.cout; a.k = ly.k; a.pad = ly.pad; a.n = (int)n; a.lpad = (int)rows_padded(lout);
     a.w = w[0]; a.bias = bvec[0]; a.out = buf[0]; a.row_stride = rows_padded(lout);
-    if (ly.cout == 32 && ly.k == 7 && ly.pad == 3)
+    const int l0_tpr = (a.lpad + kL0Pos - 1) / kL0Pos;
+    const long long l0_tiles = (long long)l0_tpr * batch;
+    AA_REQUIRE(l0_tiles < (1LL << 31) - 4096, "problem too large");
+    if (ly.cout == 32 && ly.k == 7 && ly.pad == 3 && ly.cin == 2)
+      conv_l0_reg_kernel<2><<<(unsigned)std::min<long long>(l0_tiles, 2LL * aa::num_sms()), 256, kL0Smem, stream>>>(a, l0_tpr, (int)l0_tiles);
+    else if (ly.cout == 32 && ly.k == 7 && ly.pad == 3 && ly.cin == 1)
+      conv_l0_reg_kernel<1><<<(unsigned)std::min<long long>(l0_tiles, 2LL * aa::num_sms()), 256, kL0Smem, stream>>>(a, l0_tpr, (int)l0_tiles);
+    else if (ly.cout == 32 && ly.k == 7 && ly.pad == 3)
       conv_l0_c32k7_kernel<<<dim3((unsigned)((a.lpad + kL0Pos - 1) / kL0Pos), (unsigned)batch), 256, kL0Smem, stream>>>(a);
     else
       conv_l0_kernel<<<dim3((unsigned)((a.lpad + 255) / 256), (unsigned)batch), 256, 0, stream>>>(a);
