@@ -134,7 +134,8 @@ __device__ __forceinline__ float elu1(float v) { return fmaxf(v, 0.f) + (__expf(
 
 #include "conv_ru.cuh"
 
-template <int BK>
+// RES: the layer adds a residual (ROLE_RES_SECOND); compile-time so that the epilogue carries no per-element branches
+template <int BK, bool RES>
 __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         bias_n0 = n0;
       }
-      if (a.out_f32 == nullptr && a.res != nullptr) {       // residual tile -> staging (overlaps with the MMAs)
+      if (RES && a.out_f32 == nullptr) {                    // residual tile -> staging (overlaps with the MMAs)
         for (int idx = et; idx < BM * vec_per_row; idx += 128) {
           const int rr = idx >> vpr_shift, cv = idx & (vec_per_row - 1);
           uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -292,34 +293,26 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
             }
           }
         } else {
+          // bf16 channels-last output: +bias (+ residual from staging) -> ELU (every bf16 layer of the table has one) -> staging
           const uint32_t srow = stg + (uint32_t)row_in_tile * RS + (uint32_t)c0 * 2u;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint4 rres = make_uint4(0u, 0u, 0u, 0u);
-            if (a.res != nullptr)
+            float2 y0 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(bia[8 * g + 0], bia[8 * g + 1]));
+            float2 y1 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(bia[8 * g + 2], bia[8 * g + 3]));
+            float2 y2 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bia[8 * g + 4], bia[8 * g + 5]));
+            float2 y3 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bia[8 * g + 6], bia[8 * g + 7]));
+            if (RES) {
+              uint4 rres;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres.x), "=r"(rres.y), "=r"(rres.z), "=r"(rres.w)
                            : "r"(srow + (uint32_t)g * 16u));
-            uint32_t w[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const int j = g * 8 + h * 2;
-              float x0 = 0.f, x1 = 0.f;
-              if (valid) {
-                x0 = __uint_as_float(v[j]) + bia[j];
-                x1 = __uint_as_float(v[j + 1]) + bia[j + 1];
-                if (a.res != nullptr) {
-                  const uint32_t rw = (h == 0) ? rres.x : (h == 1) ? rres.y : (h == 2) ? rres.z : rres.w;
-                  __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw);
-                  x0 += __bfloat162float(rb.x);
-                  x1 += __bfloat162float(rb.y);
-                }
-                if (a.elu) { x0 = elu1(x0); x1 = elu1(x1); }
-              }
-              __nv_bfloat162 o = __floats2bfloat162_rn(x0, x1);
-              w[h] = *reinterpret_cast<uint32_t*>(&o);
+              y0 = __fadd2_rn(y0, unpack_bf16(rres.x));
+              y1 = __fadd2_rn(y1, unpack_bf16(rres.y));
+              y2 = __fadd2_rn(y2, unpack_bf16(rres.z));
+              y3 = __fadd2_rn(y3, unpack_bf16(rres.w));
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)g * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                         "r"(w[3])
+            uint4 o = make_uint4(pack_bf16(elu2(y0)), pack_bf16(elu2(y1)), pack_bf16(elu2(y2)), pack_bf16(elu2(y3)));
+            if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)g * 16u), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
                          : "memory");
           }
         }
@@ -691,8 +684,10 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   int dev = 0;
   AA_CUDA(cudaGetDevice(&dev));
   AA_CUDA(cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
-  AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_c32k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
@@ -865,7 +860,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     a.out_row_stride = rows_padded(lout);
     a.elu = ly.elu; a.tanh_out = (last && apply_tanh) ? 1 : 0;
     const int stage_bytes = BM * p.bk * 2 + ((bn * p.bk * 2 + 1023) & ~1023);
-    a.n_epi = last ? 1 : (bn <= 64 ? 4 : (bn <= 128 ? 3 : 1));
+    a.n_epi = last ? 1 : (bn <= 64 ? 4 : (bn <= 128 ? (n_chunks_total <= 8 ? 3 : 2) : 1));
     a.n_acc = std::min(kMaxAcc, std::min(512 / bn, 2 * a.n_epi));
     const int staging = a.n_epi * ((last ? 0 : BM * (bn * 2 + 16)) + bn * 4);
     a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging) / stage_bytes));
@@ -873,8 +868,15 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     AA_REQUIRE(smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);
     const int grid = (int)std::min<long long>(a.tiles, aa::num_sms());
     const int threads = 64 + 128 * a.n_epi;
-    if (p.bk == 64) conv_tc_kernel<64><<<grid, threads, smem, stream>>>(tmA, tmB, a);
-    else conv_tc_kernel<32><<<grid, threads, smem, stream>>>(tmA, tmB, a);
+    AA_REQUIRE(last || ly.elu, "bf16 layers without ELU are not supported on the tensor-core path (layer %zu)", i);
+    const bool res = a.res != nullptr;
+    if (p.bk == 64) {
+      if (res) conv_tc_kernel<64, true><<<grid, threads, smem, stream>>>(tmA, tmB, a);
+      else conv_tc_kernel<64, false><<<grid, threads, smem, stream>>>(tmA, tmB, a);
+    } else {
+      if (res) conv_tc_kernel<32, true><<<grid, threads, smem, stream>>>(tmA, tmB, a);
+      else conv_tc_kernel<32, false><<<grid, threads, smem, stream>>>(tmA, tmB, a);
+    }
     AA_LAUNCH_CHECK();
     if (ly.role == ROLE_RES_SECOND) res_buf = -1;
     cur = dst;
