@@ -258,13 +258,26 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
         bias_n0 = n0;
       }
       if (RES && a.out_f32 == nullptr) {                    // residual tile -> staging (overlaps with the MMAs)
-        for (int idx = et; idx < BM * vec_per_row; idx += 128) {
-          const int rr = idx >> vpr_shift, cv = idx & (vec_per_row - 1);
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (m0 + rr < a.lout) v = __ldg(reinterpret_cast<const uint4*>(a.res + tile_off + (long long)rr * a.cout) + cv);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)rr * RS + (uint32_t)cv * 16u), "r"(v.x),
-                       "r"(v.y), "r"(v.z), "r"(v.w)
-                       : "memory");
+        // loads in batches of 4 before their shared-memory stores: one L2 round trip per batch, not per 16-byte piece
+        const int n_vec = BM * vec_per_row;                 // multiple of 512 (bn >= 32)
+        const __nv_bfloat16* rbase = a.res + tile_off;
+        for (int i0 = et; i0 < n_vec; i0 += 512) {
+          uint4 rv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = i0 + 128 * u;
+            const int rr = idx >> vpr_shift, cv = idx & (vec_per_row - 1);
+            rv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (m0 + rr < a.lout) rv[u] = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)rr * a.cout) + cv);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = i0 + 128 * u;
+            const int rr = idx >> vpr_shift, cv = idx & (vec_per_row - 1);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)rr * RS + (uint32_t)cv * 16u), "r"(rv[u].x),
+                         "r"(rv[u].y), "r"(rv[u].z), "r"(rv[u].w)
+                         : "memory");
+          }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
