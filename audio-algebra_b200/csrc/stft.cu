@@ -20,14 +20,17 @@
 //   * epilogues: |X|^2 -> sparse (<= 2 taps per bin) mel projection from shared memory (quarter-warp =
 //     one filter x the tile's 6 frames, packed (rowA,rowB) FFMA2, conflict-free skewed P lines), or
 //     staged power / complex stores that write 24/48-byte runs along the frame axis.
-// Generic path (any power-of-two n_fft in [64, 8192]) -- `stft_generic_kernel`: one CTA per
-//   (row, frame), shared-memory radix-2 FFT; correct for every configuration, not tuned.
+// Warp path (n_fft = 64 .. 1024, any hop / window: the reference defaults n_fft = 1024, hop = 256) -- `stft_warp_kernel`:
+//   one warp per frame of a row pair, R-point FFT in registers x 32-point FFT across lanes by shuffles.
+// Generic path (any other power-of-two n_fft up to 8192, or n_fft = 2048 with a non-Hann window / odd hop) --
+//   `stft_generic_kernel`: one CTA per (row, frame), shared-memory radix-2 FFT; correct for every configuration, not tuned.
 #include "aa_common.cuh"
 #include "fft_gen.cuh"
 #include "stft_consts.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -591,6 +594,197 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(const StftArgs a, int
   (void)n_fft;
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp kernel, n_fft = 64 R with R in {1, 2, 4, 8, 16} (n_fft 64 .. 1024: covers the reference defaults n_fft = 1024,
+// hop = 256, given_models.py:151-160,259-264): one warp = one frame of one ROW PAIR (rows packed in fp32x2 registers).
+// M = 32 R complex points, n = 32 r + lane, k = k1 + R k2:
+//   Z[k1 + R k2] = sum_l W_32^(l k2) [ W_M^(l k1) sum_r z[32 r + l] W_R^(r k1) ]
+// = an R-point FFT over the lane's registers, a twiddle, and a 32-point FFT ACROSS LANES done with shuffles (radix-2 DIF:
+// lane p ends up with k2 = bitrev5(p)).  The real-FFT split needs Z[M - k]: register R - k1 of lane p ^ 31 (k1 >= 1), or
+// register 0 of the lane holding k2' = (32 - k2) & 31 (k1 = 0).  No shared memory except the mel power line.
+// ------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void fft_regs(float2 (&re)[R], float2 (&im)[R]) {
+  if constexpr (R == 2) {
+    const float2 tr = re[1], ti = im[1];
+    re[1] = psub(re[0], tr); im[1] = psub(im[0], ti); re[0] = padd(re[0], tr); im[0] = padd(im[0], ti);
+  } else if constexpr (R == 4) {   // slots hold x0, x2, x1, x3 (bit-reversed input), natural output
+    float2 ar = padd(re[0], re[1]), ai = padd(im[0], im[1]), br = psub(re[0], re[1]), bi = psub(im[0], im[1]);
+    float2 cr = padd(re[2], re[3]), ci = padd(im[2], im[3]), dr = psub(re[2], re[3]), di = psub(im[2], im[3]);
+    re[0] = padd(ar, cr); im[0] = padd(ai, ci); re[2] = psub(ar, cr); im[2] = psub(ai, ci);
+    re[1] = padd(br, di); im[1] = psub(bi, dr);   // b + (-i) d
+    re[3] = psub(br, di); im[3] = padd(bi, dr);   // b - (-i) d
+  } else if constexpr (R == 8) {
+    fft8_dit(re, im);
+  } else if constexpr (R == 16) {
+    fft16_dit(re, im);
+  }
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(128) stft_warp_kernel(const StftArgs a, const float2* __restrict__ tw_lane,
+                                                        const float2* __restrict__ tw_split, long long n_items, int mel_w4_count) {
+  constexpr int M = 32 * R, LOGR = (R == 1) ? 0 : (R == 2) ? 1 : (R == 4) ? 2 : (R == 8) ? 3 : 4;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* P = reinterpret_cast<float2*>(smem) + warp * (M + 8);          // mel: this warp's power line (rowA, rowB) per bin
+  // mel: filter tables staged once per (persistent) block: [n_mels] start, [n_mels] count, [n_mels] offset, then the float4 weights
+  int* s_meta = reinterpret_cast<int*>(reinterpret_cast<float2*>(smem) + 4 * (M + 8));
+  float4* s_w4 = reinterpret_cast<float4*>(s_meta + ((3 * a.n_mels + 3) & ~3));
+  if constexpr (MODE == MODE_MEL) {
+    for (int i = threadIdx.x; i < 3 * a.n_mels; i += 128) s_meta[i] = __ldg(a.mel_start4 + i);   // start | cnt | off are contiguous
+    for (int i = threadIdx.x; i < mel_w4_count; i += 128) s_w4[i] = __ldg(a.mel_w4 + i);
+    __syncthreads();
+  }
+  // per-lane twiddles of the 5 lane-FFT stages (distance s = 16, 8, 4, 2, 1): upper lanes (lane & s) multiply by W_{2s}^(lane & (s-1))
+  float2 stw[5];
+  float ssg[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int sdist = 16 >> q;
+    const bool upper = (lane & sdist) != 0;
+    float sn, cs;
+    sincospif(-(float)(lane & (sdist - 1)) / (float)sdist, &sn, &cs);
+    stw[q] = upper ? make_float2(cs, sn) : make_float2(1.f, 0.f);
+    ssg[q] = upper ? -1.f : 1.f;
+  }
+  const int k2 = (int)(__brev((unsigned)lane) >> 27);
+  const int src0 = (int)(__brev((unsigned)((32 - k2) & 31)) >> 27);   // lane that holds k2' = (32 - k2) & 31
+  const bool center = a.center_off != 0;
+  const long long n_freq = a.n_freq;
+  const bool vec_ok = a.wav_aligned16 && (a.n_in & 1) == 0 && (a.hop & 1) == 0;
+
+  for (long long item = (long long)blockIdx.x * 4 + warp; item < n_items; item += (long long)gridDim.x * 4) {
+    const long long pair = item / a.n_frames;
+    const int frame = (int)(item - pair * a.n_frames);
+    const long long rowA = 2 * pair;
+    const bool hasB = rowA + 1 < a.rows;
+    const float* __restrict__ pa = a.wav + rowA * a.n_in;
+    const float* __restrict__ pb = hasB ? pa + a.n_in : nullptr;
+    const long long s0 = (long long)frame * a.hop - a.center_off;
+    float2 re[R], im[R];
+    if (vec_ok && hasB && s0 >= 0 && s0 + 2 * M <= a.n_in) {   // interior frame: 8-byte loads of (x[2n], x[2n+1])
+      const float2* FA = reinterpret_cast<const float2*>(pa + s0);
+      const float2* FB = reinterpret_cast<const float2*>(pb + s0);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int n = 32 * r + lane;
+        const float2 w = __ldg(a.window2 + n);
+        const float2 xa = __ldg(FA + n), xb = __ldg(FB + n);
+        const int slot = (LOGR == 0) ? 0 : (int)(__brev((unsigned)r) >> (32 - (LOGR == 0 ? 1 : LOGR)));
+        re[slot] = make_float2(xa.x * w.x, xb.x * w.x);
+        im[slot] = make_float2(xa.y * w.y, xb.y * w.y);
+      }
+    } else {                                                    // chunk borders: reflect padding, zero_pad_po2 tail, odd last row
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int n = 32 * r + lane;
+        const float2 w = __ldg(a.window2 + n);
+        const float xa0 = fetch_sample(pa, s0 + 2 * n, a.n_in, a.n_pad, center), xa1 = fetch_sample(pa, s0 + 2 * n + 1, a.n_in, a.n_pad, center);
+        const float xb0 = fetch_sample(pb, s0 + 2 * n, a.n_in, a.n_pad, center), xb1 = fetch_sample(pb, s0 + 2 * n + 1, a.n_in, a.n_pad, center);
+        const int slot = (LOGR == 0) ? 0 : (int)(__brev((unsigned)r) >> (32 - (LOGR == 0 ? 1 : LOGR)));
+        re[slot] = make_float2(xa0 * w.x, xb0 * w.x);
+        im[slot] = make_float2(xa1 * w.y, xb1 * w.y);
+      }
+    }
+    fft_regs<R>(re, im);                       // slot k1: sum_r z[32 r + lane] W_R^(r k1)
+#pragma unroll
+    for (int k1 = 1; k1 < R; ++k1) {           // twiddle W_M^(lane k1)
+      const float2 tw = __ldg(tw_lane + k1 * 32 + lane);
+      const float2 r_ = re[k1], i_ = im[k1];
+      re[k1] = pfma(i_, -tw.y, pmuls(r_, tw.x));
+      im[k1] = pfma(i_, tw.x, pmuls(r_, tw.y));
+    }
+    // ---- 32-point FFT across lanes, radix-2 DIF: lower lane: a + b; upper lane: (a_lower - a_upper) W ----
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int sdist = 16 >> q;
+#pragma unroll
+      for (int k1 = 0; k1 < R; ++k1) {
+        const float2 orr = make_float2(__shfl_xor_sync(0xffffffffu, re[k1].x, sdist), __shfl_xor_sync(0xffffffffu, re[k1].y, sdist));
+        const float2 oi = make_float2(__shfl_xor_sync(0xffffffffu, im[k1].x, sdist), __shfl_xor_sync(0xffffffffu, im[k1].y, sdist));
+        const float2 dr = pfma(re[k1], ssg[q], orr), di = pfma(im[k1], ssg[q], oi);   // lower: mine + other; upper: other - mine
+        if (q < 4) {
+          re[k1] = pfma(di, -stw[q].y, pmuls(dr, stw[q].x));
+          im[k1] = pfma(di, stw[q].x, pmuls(dr, stw[q].y));
+        } else {
+          re[k1] = dr; im[k1] = di;
+        }
+      }
+    }
+    // lane holds Z[k1 + R k2], k2 = bitrev5(lane).  Real-FFT split: 2 X[k] = (Z[k] + conj Z[M-k]) - i W_{2M}^k (Z[k] - conj Z[M-k])
+    float* outA = a.out;
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) {
+      const int kp = (k1 == 0) ? 0 : R - k1;                 // partner register
+      float2 br, bi;
+      if (k1 == 0) {
+        br = make_float2(__shfl_sync(0xffffffffu, re[0].x, src0), __shfl_sync(0xffffffffu, re[0].y, src0));
+        bi = make_float2(__shfl_sync(0xffffffffu, im[0].x, src0), __shfl_sync(0xffffffffu, im[0].y, src0));
+      } else {
+        br = make_float2(__shfl_xor_sync(0xffffffffu, re[kp].x, 31), __shfl_xor_sync(0xffffffffu, re[kp].y, 31));
+        bi = make_float2(__shfl_xor_sync(0xffffffffu, im[kp].x, 31), __shfl_xor_sync(0xffffffffu, im[kp].y, 31));
+      }
+      const int k = k1 + R * k2;
+      const float2 tw = __ldg(tw_split + k);                 // W_{2M}^k
+      const float2 ar = re[k1], ai = im[k1];
+      const float2 e_r = padd(ar, br), e_i = psub(ai, bi);   // E2 = a + conj(b)
+      const float2 o_r = padd(ai, bi), o_i = psub(br, ar);   // O2 = (a - conj(b)) / i
+      float2 xr = pmuls(pfma(o_i, -tw.y, pfma(o_r, tw.x, e_r)), 0.5f);
+      float2 xi = pmuls(pfma(o_r, tw.y, pfma(o_i, tw.x, e_i)), 0.5f);
+      if (k == 0) { xr = padd(ar, ai); xi = make_float2(0.f, 0.f); }   // DC
+      if constexpr (MODE == MODE_COMPLEX) {
+        float2* o = reinterpret_cast<float2*>(outA) + (rowA * n_freq + k) * a.n_frames + frame;
+        o[0] = make_float2(xr.x, xi.x);
+        if (hasB) o[n_freq * a.n_frames] = make_float2(xr.y, xi.y);
+      } else {
+        const float2 pw = pfma2(xi, xi, pmul(xr, xr));
+        if constexpr (MODE == MODE_POWER) {
+          float* o = outA + (rowA * n_freq + k) * a.n_frames + frame;
+          o[0] = pw.x;
+          if (hasB) o[n_freq * a.n_frames] = pw.y;
+        } else {
+          P[k] = pw;
+        }
+      }
+    }
+    if (lane == 0) {   // Nyquist bin M = Re Z[0] - Im Z[0] (lane 0 holds k2 = 0)
+      const float2 ny = psub(re[0], im[0]);
+      if constexpr (MODE == MODE_COMPLEX) {
+        float2* o = reinterpret_cast<float2*>(outA) + (rowA * n_freq + M) * a.n_frames + frame;
+        o[0] = make_float2(ny.x, 0.f);
+        if (hasB) o[n_freq * a.n_frames] = make_float2(ny.y, 0.f);
+      } else if constexpr (MODE == MODE_POWER) {
+        float* o = outA + (rowA * n_freq + M) * a.n_frames + frame;
+        o[0] = ny.x * ny.x;
+        if (hasB) o[n_freq * a.n_frames] = ny.y * ny.y;
+      } else {
+        P[M] = pmul(ny, ny);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) P[M + j] = make_float2(0.f, 0.f);
+      }
+    }
+    if constexpr (MODE == MODE_MEL) {
+      __syncwarp();
+      for (int m = lane; m < a.n_mels; m += 32) {
+        const int start = s_meta[m], cnt = s_meta[a.n_mels + m];
+        const float4* w4 = s_w4 + s_meta[2 * a.n_mels + m];      // weights x 0.25 (the fast kernel's P holds 4|X|^2)
+        float2 acc = make_float2(0.f, 0.f);
+        for (int j = 0; j < cnt; ++j) {
+          const float4 w = w4[j];
+          const float2* pp = P + start + 4 * j;
+          acc = pfma(pp[0], w.x, acc); acc = pfma(pp[1], w.y, acc);
+          acc = pfma(pp[2], w.z, acc); acc = pfma(pp[3], w.w, acc);
+        }
+        float* o = outA + (rowA * a.n_mels + m) * a.n_frames + frame;
+        o[0] = 4.0f * acc.x;
+        if (hasB) o[(long long)a.n_mels * a.n_frames] = 4.0f * acc.y;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // MagDPhaseSpectrogramAE epilogue (given_models.py:214-231)
 __global__ void magdphase_kernel(const float2* __restrict__ spec, long long cf, int n_frames, long long half_elems,
                                  float* __restrict__ out) {
@@ -623,10 +817,13 @@ struct AaStftPlan {
   float2* d_tw2 = nullptr;
   int* d_mel_meta = nullptr;   // start4 | cnt4 | off4
   float4* d_mel_w4 = nullptr;
+  int mel_w4_count = 0;
   int4* d_mel_steps = nullptr;   // fast path mel step lists followed by the step weights
   float* d_lane_consts = nullptr;
   int mel_steps_per_warp = 0, mel_hdr_bytes = 0, mel_w_bytes = 0;
   int fast_smem = 0, fast_grid_per_sm = 2;
+  float2* d_wk = nullptr;        // warp kernel (n_fft <= 1024): [R][32] W_M^(lane k1), then [M] W_2M^k
+  int wk_r = 0;
   // resources of aa_stft_mel_f32_host (created lazily)
   cudaStream_t hstream[2] = {nullptr, nullptr};
   float* hbuf_in[2] = {nullptr, nullptr};
@@ -698,6 +895,22 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
   AA_CUDA(cudaMemcpy(p->d_tw1, tw1.data(), sizeof(float2) * tw1.size(), cudaMemcpyHostToDevice));
   AA_CUDA(cudaMalloc(&p->d_tw2, sizeof(float2) * tw2.size()));
   AA_CUDA(cudaMemcpy(p->d_tw2, tw2.data(), sizeof(float2) * tw2.size(), cudaMemcpyHostToDevice));
+  if (!p->fast && n_fft <= 1024 && getenv("AA_STFT_CTA_KERNEL") == nullptr) {
+    const int R = n_fft / 64;
+    std::vector<float2> wk((size_t)R * 32 + M);
+    for (int k1 = 0; k1 < R; ++k1)
+      for (int l = 0; l < 32; ++l) {
+        const double th = -2.0 * PI * (double)(k1 * l) / (double)M;
+        wk[(size_t)k1 * 32 + l] = make_float2((float)std::cos(th), (float)std::sin(th));
+      }
+    for (int k = 0; k < M; ++k) {
+      const double th = -PI * (double)k / (double)M;
+      wk[(size_t)R * 32 + k] = make_float2((float)std::cos(th), (float)std::sin(th));
+    }
+    AA_CUDA(cudaMalloc(&p->d_wk, sizeof(float2) * wk.size()));
+    AA_CUDA(cudaMemcpy(p->d_wk, wk.data(), sizeof(float2) * wk.size(), cudaMemcpyHostToDevice));
+    p->wk_r = R;
+  }
   // mel filterbank -> per-filter (start4, cnt4, off4) + float4-aligned weights (x 0.25)
   if (n_mels > 0) {
     const int F = p->n_freq;
@@ -736,6 +949,7 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
     if (w.empty()) w.resize(4, 0.f);
     AA_CUDA(cudaMalloc(&p->d_mel_meta, sizeof(int) * meta.size()));
     AA_CUDA(cudaMemcpy(p->d_mel_meta, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice));
+    p->mel_w4_count = (int)(w.size() / 4);
     AA_CUDA(cudaMalloc(&p->d_mel_w4, sizeof(float) * w.size()));
     AA_CUDA(cudaMemcpy(p->d_mel_w4, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
     if (p->fast) {
@@ -820,7 +1034,7 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
 
 int aa_stft_plan_destroy(AaStftPlan* p) {
   if (!p) return AA_OK;
-  cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4); cudaFree(p->d_mel_steps); cudaFree(p->d_lane_consts);
+  cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4); cudaFree(p->d_mel_steps); cudaFree(p->d_lane_consts); cudaFree(p->d_wk);
   for (int i = 0; i < 2; ++i) {
     if (p->hbuf_in[i]) cudaFree(p->hbuf_in[i]);
     if (p->hbuf_out[i]) cudaFree(p->hbuf_out[i]);
@@ -884,6 +1098,26 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
   } else {
     a.tiles_per_pair = 0; a.n_tiles = 0; a.mel_steps = nullptr; a.mel_steps_per_warp = 0;
     a.mel_hdr_bytes = a.mel_w_bytes = 0; a.lane_consts = nullptr;
+    if (p->wk_r > 0) {
+      const int R = p->wk_r;
+      const long long n_items = ((rows + 1) / 2) * n_frames;
+      const unsigned wgrid = (unsigned)std::min<long long>((n_items + 3) / 4, (long long)aa::num_sms() * 16);
+      const int wsmem = (mode == MODE_MEL) ? 4 * (32 * R + 8) * 8 + ((3 * p->n_mels + 3) & ~3) * 4 + p->mel_w4_count * 16 : 0;
+      AA_REQUIRE(wsmem <= 48 * 1024, "mel filterbank too large for the warp STFT kernel (%d bytes)", wsmem);
+      const int w4c = p->mel_w4_count;
+      const float2* twl = p->d_wk;
+      const float2* tws = p->d_wk + (size_t)R * 32;
+#define AA_WK(RR)                                                                                                        \
+  do {                                                                                                                   \
+    if (mode == MODE_COMPLEX) stft_warp_kernel<RR, MODE_COMPLEX><<<wgrid, 128, wsmem, st>>>(a, twl, tws, n_items, w4c);  \
+    else if (mode == MODE_POWER) stft_warp_kernel<RR, MODE_POWER><<<wgrid, 128, wsmem, st>>>(a, twl, tws, n_items, w4c); \
+    else stft_warp_kernel<RR, MODE_MEL><<<wgrid, 128, wsmem, st>>>(a, twl, tws, n_items, w4c);                          \
+  } while (0)
+      if (R == 1) AA_WK(1); else if (R == 2) AA_WK(2); else if (R == 4) AA_WK(4); else if (R == 8) AA_WK(8); else AA_WK(16);
+#undef AA_WK
+      AA_LAUNCH_CHECK();
+      return AA_OK;
+    }
     const int64_t grid = rows * n_frames;
     AA_REQUIRE(grid < (1LL << 31), "grid too large (%lld frames)", (long long)grid);
     const int M = p->n_fft / 2, smem = M * 12 + 64;
