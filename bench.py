@@ -313,7 +313,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "kernel": "stft2048_kernel<MEL>", "kernel_us": 1e3 * k_ms,
                          "algorithmic_bytes": ALG_BYTES, "peak_source": peak_src,
-                         "note": "fp32 FFT math + shared-memory exchange bound, not HBM bound (DESIGN.md)"},
+                         # SURVEY.md 8d asks for the FP32 view next to the (judged) HBM view: 131 584 frame-channels x
+                         # (56 kFLOP real FFT + 3 k power + 4 k sparse mel) = 8.29 GFLOP against 148 SM x 128 lanes x 2 x 1.965 GHz
+                         "fp32_tflops": 8.29e9 * (BATCH / 256) / (k_ms * 1e-3) / 1e12, "fp32_peak_tflops": 74.46,
+                         "fp32_frac": 8.29e9 * (BATCH / 256) / (k_ms * 1e-3) / 1e12 / 74.46,
+                         "note": "latency / lock-step bound: FP32 pipe 47 %, issue 44 %, shared-memory pipe 70 % busy under ncu (DESIGN.md 4.1); not HBM bound"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_extras:

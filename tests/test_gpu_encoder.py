@@ -135,3 +135,20 @@ def test_bf16_fused_residual_units_match_layerwise(setup):
         a, b = fused.encode(x), layerwise.encode(x)
         assert tuple(a.shape) == tuple(b.shape)
         assert rel_l2(a, b.cpu()) < 1.5e-2, (shape, rel_l2(a, b.cpu()))
+
+
+def test_fused_fader_mix_three_and_four_stems(setup):
+    "layer 0 sums up to four fader-scaled stems in its load (get_stems_faders maxstems > 2): fp32 and bf16 paths"
+    aab, O, enc_o, dv = setup
+    stems = [_x((2, 2, 6000), 30 + i) for i in range(4)]
+    f = [1.4630, -0.5718, 0.8112, -1.2031]
+    dvb = aab.DVAEWrapper(debug=False, compute_dtype="bf16")
+    dvb.model.load_oracle_weights(enc_o)
+    dvb = dvb.cuda()
+    for n in (3, 4):
+        ref = O.dvae_encode(enc_o, sum(fi * si for fi, si in zip(f[:n], stems[:n])))
+        y = dv.model.encode_mix([s.cuda() for s in stems[:n]], f[:n])
+        assert rel_l2(y, ref) < 1e-3, n
+        yb = dvb.model.encode_mix([s.cuda() for s in stems[:n]], f[:n]).cpu().double()
+        cos = torch.nn.functional.cosine_similarity(yb.flatten(1), ref.double().flatten(1), dim=1)
+        assert cos.min().item() >= 0.999, (n, cos)
