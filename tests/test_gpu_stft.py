@@ -198,3 +198,28 @@ def test_mel_filterbank_variants(aab):
     x2 = torch.rand(3, 1, 20000, generator=g) - 0.5
     m = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512)
     assert rel_l2(m.encode(x2.cuda()), O.mel_spectrogram(x2, 48000, 2048, 512)) < TOL
+
+
+@pytest.mark.parametrize("n_fft,hop,shape", [(64, 16, (2, 2, 1000)), (128, 32, (3, 1, 777)), (256, 100, (1, 2, 5000)), (512, 128, (5, 1, 4096)),
+                                             (1024, 256, (3, 2, 20000)), (1024, 200, (1, 3, 9001)), (1024, 1024, (2, 2, 8192))])
+def test_warp_kernel_small_n_fft(aab, n_fft, hop, shape):
+    """n_fft <= 1024 (incl. the reference defaults 1024 / 256, given_models.py:151-160) runs on the warp kernel (register FFT x
+    shuffle FFT across lanes, row pairs packed): every R = n_fft / 64, odd row counts, odd lengths (unaligned rows, zero_pad_po2
+    tails, reflect edges), odd hops, a non-Hann window and center=False, against the float64 oracle."""
+    O = _oracle()
+    g = torch.Generator().manual_seed(n_fft * 7 + hop)
+    x = torch.rand(*shape, generator=g) * 2 - 1
+    xc = x.cuda()
+    assert rel_l2(aab.SpectrogramAE(n_fft=n_fft, hop_length=hop).encode(xc), O.stft_complex(x, n_fft, hop)) < TOL
+    assert rel_l2(aab.MagSpectrogramAE(n_fft=n_fft, hop_length=hop).encode(xc), O.power_spectrogram(x, n_fft, hop)) < TOL
+    if n_fft >= 256:
+        assert rel_l2(aab.MelSpectrogramAE(sample_rate=48000, n_fft=n_fft, hop_length=hop, n_mels=40).encode(xc),
+                      O.mel_spectrogram(x, 48000, n_fft, hop, n_mels=40)) < TOL
+    w = torch.hamming_window(n_fft)
+    out = aab.MagSpectrogramAE(n_fft=n_fft, hop_length=hop, window_fn=torch.hamming_window).encode(xc)
+    assert rel_l2(out, O.power_spectrogram(x, n_fft, hop, window=w.double())) < TOL
+    m = aab.SpectrogramAE(n_fft=n_fft, hop_length=hop, center=False)
+    m.zero_pad = False
+    ref = O.stft_complex(x, n_fft, hop, center=False, zero_pad=False)
+    out = m.encode(xc)
+    assert tuple(out.shape) == tuple(ref.shape) and rel_l2(out, ref) < TOL
