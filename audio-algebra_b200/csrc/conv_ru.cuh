@@ -73,11 +73,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
-// ELU(alpha = 1) of a pair: max(t, 2^(min(t log2 e, 0)) - 1)
+// ELU(alpha = 1) of a pair: max(t, 2^(-|t| log2 e) - 1).  For t <= 0 this is exp(t) - 1 >= t; for t > 0 the second term lies in
+// (-1, 0) < t.  The |t| and the sign ride on the FMUL operand modifiers: no clamp instructions.
 __device__ __forceinline__ float2 elu2(float2 t) {
-  float2 e = __fmul2_rn(t, make_float2(1.4426950408889634f, 1.4426950408889634f));
-  e.x = fminf(e.x, 0.f);
-  e.y = fminf(e.y, 0.f);
+  float2 e = make_float2(__fmul_rn(-fabsf(t.x), 1.4426950408889634f), __fmul_rn(-fabsf(t.y), 1.4426950408889634f));
   asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e.x));
   asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e.y));
   e = __fadd2_rn(e, make_float2(-1.f, -1.f));

@@ -191,6 +191,27 @@ def run_extras(dev):
     out["mixer_train_step"] = {"ms": ms, "batch": Bm, "chunk_samples": Nm, "stems": 2, "encoder_passes": 4,
                                "audio_s_per_s": Bm * Nm / SR / (ms * 1e-3),
                                "note": "train_aa_mixer_accel step: do_mixing (3 encodes) + batch encode, projector fwd/bwd, 4 loss terms, flat Adam"}
+    del stems, trainer
+    # ---- config 4: effects step (4 encodes as one 4B batch + projector + guesses + losses, fwd + bwd) and PCA accumulation ----
+    Be = 256
+    batch = {k: torch.rand(Be, 2, Nm, generator=g, device=dev) - 0.5 for k in ("a1", "b1", "a2", "b2")}
+    aa2 = aab.aa_effects.AudioAlgebra(64, 64).cuda()
+
+    def effects_step():
+        for p_ in aa2.parameters():
+            p_.grad = None
+        arch = aab.aa_effects.do_mixing(batch, dvb.model, aa2, dev)
+        aab.aa_effects.effects_losses(arch)["loss"].backward()
+
+    ms = timed(effects_step, 3, warm=1)
+    out["effects_step"] = {"ms": ms, "batch": Be, "chunk_samples": Nm, "audio_s_per_s": 4 * Be * Nm / SR / (ms * 1e-3),
+                           "note": "train_aa_effects step: a1,b1,a2,b2 encoded as one 4B batch, projector enc/dec, effect guesses, 4 loss terms, backward"}
+    from audio_algebra_b200.pca import RunningCovariance
+    ys = torch.tanh(torch.randn(Be, 64, Nm // 128, generator=g, device=dev))
+    rc = RunningCovariance(64, dev)
+    ms = timed(lambda: rc.update(ys), 10)
+    out["pca_accumulate"] = {"ms": ms, "latents": list(ys.shape), "GBps": ys.numel() * 4 / ms / 1e6, "hbm_frac": ys.numel() * 4 / ms / 1e6 / hbm,
+                             "note": "calc_effects_pca loop body: 64x64 scatter straight from [B,64,T'] latents (reads them once)"}
     return out
 
 
