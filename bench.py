@@ -172,9 +172,9 @@ def run_extras(dev):
     del x
     # ---- conv encoder, bf16 tcgen05 path (config 5 encode sweep point): 68.17 GFLOP per 2^17-sample chunk ----
     dvb = aab.DVAEWrapper(debug=False, compute_dtype="bf16").cuda()
-    for B in (64, 256):
+    for B in (64, 256, 1024):          # points of the config-5 encode sweep
         xe = synth(B, 99, dev)
-        ms = timed(lambda: dvb.encode(xe), 5)
+        ms = timed(lambda: dvb.encode(xe), 5 if B <= 256 else 3)
         tf = B * 68.17 / ms            # GFLOP / ms = TFLOP/s
         out[f"encoder_bf16_B{B}"] = {"ms": ms, "tflops": tf, "frac_of_bf16_burst_peak": tf / burst, "frac_of_bf16_sustained_peak": tf / sustained,
                                      "peak_source": src, "audio_s_per_s": B * CHUNK / SR / (ms * 1e-3), "chunk_samples": CHUNK,
