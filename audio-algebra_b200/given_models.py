@@ -16,7 +16,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 
-__all__ = ['GivenModelClass', 'SpectrogramAE', 'MagSpectrogramAE', 'MagDPhaseSpectrogramAE', 'MelSpectrogramAE', 'DVAEWrapper']
+__all__ = ['encode_all', 'GivenModelClass', 'SpectrogramAE', 'MagSpectrogramAE', 'MagDPhaseSpectrogramAE', 'MelSpectrogramAE', 'DVAEWrapper']
 
 
 class GivenModelClass(nn.Module):
@@ -352,3 +352,63 @@ class DVAEWrapper(GivenModelClass):
         on_cpu = not waveform.is_cuda
         reps = self.model.encode_it(waveform)
         return reps.cpu() if on_cpu else reps
+
+
+def encode_all(given_model, data, batch_size=64, out=None, device=None):
+    """Bulk encode loop of the reference (xae_dataset.ipynb cell 50 `encode_all`, effects_explorer.ipynb cell 36):
+
+        reps[i:i+bs] = given_model.encode(data[i:i+bs].to(device)).cpu()
+
+    with the three stages overlapped instead of run back to back: batch i+1 is copied host->device (from pinned
+    staging, on a copy stream) while batch i is encoded, and the representations of batch i-1 return to the host
+    on a third stream.  Encodes stay on ONE stream (a model's kernels share one workspace).  `data`: CPU tensor
+    [Ntot, C, N]; `out`: optional preallocated CPU tensor [Ntot, ...] (pinned memory makes the return copy
+    asynchronous); returns it."""
+    if data.is_cuda:
+        raise ValueError("encode_all takes the host-resident dataset tensor; call given_model.encode for device tensors")
+    dev = torch.device(device) if device is not None else next((p.device for p in given_model.parameters() if p.is_cuda),
+                                                               torch.device("cuda", torch.cuda.current_device()))
+    n = data.shape[0]
+    data = data.float() if data.dtype != torch.float32 else data
+    with torch.cuda.device(dev):
+        compute = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        bs = max(1, min(int(batch_size), max(n, 1)))
+        pinned = None if data.is_pinned() else [torch.empty((bs,) + tuple(data.shape[1:]), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        d_in = [torch.empty((bs,) + tuple(data.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]      # H2D of slot s finished (its pinned buffer may be refilled)
+        ev_free = [torch.cuda.Event() for _ in range(2)]     # the encode that read d_in[s] finished
+        used = [False, False]
+        for i, lo in enumerate(range(0, n, bs)):
+            hi, s = min(lo + bs, n), i & 1
+            nb = hi - lo
+            if pinned is not None:
+                if used[s]:
+                    ev_h2d[s].synchronize()
+                pinned[s][:nb].copy_(data[lo:hi])
+                src = pinned[s][:nb]
+            else:
+                src = data[lo:hi]
+            with torch.cuda.stream(s_in):
+                if used[s]:
+                    s_in.wait_event(ev_free[s])
+                d_in[s][:nb].copy_(src, non_blocking=True)
+                ev_h2d[s].record(s_in)
+            compute.wait_event(ev_h2d[s])
+            with torch.no_grad():
+                reps = given_model.encode(d_in[s][:nb])
+            ev_free[s].record(compute)
+            used[s] = True
+            if out is None:
+                out = torch.empty((n,) + tuple(reps.shape[1:]), dtype=reps.dtype, pin_memory=True)
+            ev_done = torch.cuda.Event()
+            ev_done.record(compute)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done)
+                out[lo:hi].copy_(reps, non_blocking=True)
+            reps.record_stream(s_out)
+        s_out.synchronize()
+        compute.synchronize()
+    if out is None:   # empty dataset
+        out = given_model.encode(data.to(dev)).cpu()
+    return out

@@ -180,6 +180,20 @@ def run_extras(dev):
                                      "peak_source": src, "audio_s_per_s": B * CHUNK / SR / (ms * 1e-3), "chunk_samples": CHUNK,
                                      "note": "SoundStreamXL-style encoder restated per SURVEY.md Appendix A (random init); bf16 operands, fp32 accumulate"}
         del xe
+    # ---- bulk encode loop end to end (xae_dataset.ipynb cell 50): host dataset -> pinned staging -> H2D / encode / D2H overlapped ----
+    nb_tot, nb = 512, 128
+    data_h = torch.empty(nb_tot, 2, CHUNK, dtype=torch.float32, pin_memory=True)
+    data_h.copy_(synth(nb_tot, 5, dev))
+    reps_h = torch.empty(nb_tot, 64, CHUNK // 128, dtype=torch.float32, pin_memory=True)
+    aab.encode_all(dvb, data_h[:nb], batch_size=nb, out=reps_h[:nb])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    aab.encode_all(dvb, data_h, batch_size=nb, out=reps_h)
+    dt = time.perf_counter() - t0
+    out["encoder_bf16_bulk_e2e"] = {"ms": 1e3 * dt, "chunks": nb_tot, "batch": nb, "audio_s_per_s": nb_tot * CHUNK / SR / dt,
+                                    "h2d_bytes": data_h.numel() * 4, "d2h_bytes": reps_h.numel() * 4,
+                                    "note": "encode_all(DVAEWrapper bf16, pinned host dataset [512,2,131072]) wall clock incl. H2D and D2H (three streams)"}
+    del data_h, reps_h
     # ---- one mixer training step (config 3: 2 stems, batch 512 x 2^16 samples, bf16 encoder, fp32 projector / losses / Adam) ----
     Bm, Nm = 512, 65536
     torch.manual_seed(2)

@@ -152,3 +152,21 @@ def test_fused_fader_mix_three_and_four_stems(setup):
         yb = dvb.model.encode_mix([s.cuda() for s in stems[:n]], f[:n]).cpu().double()
         cos = torch.nn.functional.cosine_similarity(yb.flatten(1), ref.double().flatten(1), dim=1)
         assert cos.min().item() >= 0.999, (n, cos)
+
+
+def test_encode_all_bulk_loop_matches_batch_by_batch(setup):
+    """xae_dataset.ipynb cell 50: reps[i:i+bs] = given_model.encode(data[i:i+bs].to(device)).cpu() -- the pipelined loop
+    (H2D / encode / D2H on three streams, pinned staging) returns exactly what the sequential loop returns, for a ragged
+    last batch, pageable and pinned inputs, a preallocated output, and for an STFT given model as well."""
+    aab, O, enc_o, dv = setup
+    data = _x((11, 2, 4096), 40)
+    ref = torch.cat([dv.encode(data[i:i + 4].cuda()).cpu() for i in range(0, 11, 4)], dim=0)
+    out = aab.encode_all(dv, data, batch_size=4)
+    assert out.device.type == "cpu" and torch.equal(out, ref)
+    pre = torch.empty_like(ref).pin_memory()
+    out2 = aab.encode_all(dv, data.pin_memory(), batch_size=5, out=pre)
+    assert out2 is pre and rel_l2(out2, ref) < 1e-6
+    mel = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512)
+    refm = mel.encode(data.cuda()).cpu()
+    assert torch.equal(aab.encode_all(mel, data, batch_size=3), refm)
+    assert rel_l2(ref[:4], O.dvae_encode_it(enc_o, data[:4])) < 1e-3
