@@ -60,17 +60,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Blocking wait: try_wait with a suspend-time hint lets the hardware park the thread until the phase completes (or the
+// hint expires) instead of returning at once -- without it the waiting warps (producer, MMA issuer, idle epilogue groups)
+// burn more than half of the SM's issue slots on SYNCS / BRA / YIELD polling, slots the epilogue warps need.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "TC_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra TC_DONE;\n"
       "bra TC_WAIT;\n"
       "TC_DONE:\n"
       "}\n" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
