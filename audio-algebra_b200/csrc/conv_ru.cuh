@@ -1,6 +1,6 @@
 // Fused ResidualUnit of the conv encoder on tcgen05 (included by conv_tc.cu, inside its anonymous namespace):
 //
-//     y = ELU( x + Conv1d_k1( ELU( Conv1d_k7,dilation d (x) + b7 ) ) + b1 )          (C -> C -> C channels, C = 32 / 64)
+//     y = ELU( x + Conv1d_k1( ELU( Conv1d_k7,dilation d (x) + b7 ) ) + b1 )          (C -> C -> C channels, C = 32 / 64 / 128)
 //
 // i.e. the two layers ROLE_RES_FIRST / ROLE_RES_SECOND of the layer table (ResidualUnit) in ONE
 // kernel: the intermediate never leaves the SM, x is read from HBM once (it also serves as the residual) and the
@@ -10,7 +10,8 @@
 // (UMMA canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO)) with SBO = 128 B, LBO = panel stride).  Rows are uniformly
 // 16 B apart inside a panel, so the A operand of filter tap j is the SAME x tile with the descriptor start address
 // advanced by j*d rows: every x tile (128 + 6 d rows) is loaded once for all 7 taps.  The k7 and k1 weights stay
-// resident in shared memory for the whole (persistent) kernel.
+// resident in shared memory for the whole (persistent) kernel (C = 32 / 64); at C = 128 the 229 KB of k7 weights stream
+// through a two-stage ring filled by a third producer warp (one [C][64 K] chunk per stage).
 //
 // Warp roles (64 + 128 NG threads): warp 0 = x-tile producer (16-byte cp.async straight into the panel layout, zero fill =
 // conv padding), warp 1 = tcgen05.mma issuer (k7 of tile i+1 is issued before k1 of tile i: the tensor pipe works
@@ -34,22 +35,26 @@ struct RuArgs {
 template <int C>
 struct RuCfg {
   static constexpr int P = C / 8;                        // 16-byte channel panels per row
-  static constexpr int RA = (C == 64) ? 185 : 186;       // rows allocated per x tile (>= 128 + 6*9); odd / = 2 mod 8:
+  static constexpr bool STREAM = (C == 128);             // k7 weights (229 KB at C = 128) streamed through a ring instead of resident
+  static constexpr int RA = (C == 32) ? 186 : 185;       // rows allocated per x tile (>= 128 + 6*9); = 2 mod 8 / odd:
                                                          // the producer's 16-byte pieces then spread over all banks
   static constexpr int XS = RA * 16;                     // x panel stride (bytes)
   static constexpr int XBYTES = P * XS;
-  static constexpr int WS = C * 16;                      // weight panel stride
-  static constexpr int W7BYTES = 7 * P * WS;
+  static constexpr int WS = C * 16 + (STREAM ? 16 : 0);  // weight panel stride (+16: the streaming producer writes 8 panels per row at once)
+  static constexpr int NW = 2;                           // ring stages of streamed k7 weights
+  static constexpr int WCH = 8 * WS;                     // one streamed chunk: [C out-channels][64 K] = 8 panels
+  static constexpr int W7BYTES = STREAM ? NW * WCH : 7 * P * WS;
   static constexpr int W1BYTES = P * WS;
-  static constexpr int TS = 2048 + (C == 64 ? 16 : 32);  // intermediate / staging panel stride (copy-out conflict free)
+  static constexpr int TS = 2048 + (C == 32 ? 32 : 16);  // intermediate / staging panel stride (copy-out conflict free)
   static constexpr int TBYTES = P * TS;
   static constexpr int OFF_BIAS = 256;
-  static constexpr int OFF_W7 = 1024;
+  static constexpr int OFF_W7 = 2048;
   static constexpr int OFF_W1 = OFF_W7 + W7BYTES;
   static constexpr int OFF_X = OFF_W1 + W1BYTES;
   static constexpr int NG = 2;                           // epilogue groups (4 warps each); C = 32 runs two CTAs per SM instead
-  static constexpr int THREADS = 64 + 128 * NG;
-  static constexpr int NX = (C == 64) ? 4 : 6;           // x tiles in flight (> NG: a stage is held until its tile's phase 2 has read the residual)
+  static constexpr int EPI0 = STREAM ? 3 : 2;            // first epilogue warp (warp 0: x producer, 1: MMA issuer, 2: weight producer if STREAM)
+  static constexpr int THREADS = 32 * EPI0 + 128 * NG;
+  static constexpr int NX = (C == 32) ? 6 : (C == 64) ? 4 : 2;   // x tiles in flight (a stage is held until its tile's phase 2 has read the residual)
   // the 1x1 conv of tile i is issued after the k7 conv of tile i + LAG; LAG <= NX - 1, otherwise the x stage that tile
   // i + LAG needs would only be released by a phase 2 that waits for that very 1x1 conv
   static constexpr int LAG = (NG - 1 < NX - 1) ? NG - 1 : NX - 1;
@@ -112,7 +117,9 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
   auto tfull = [&](int g) { return base + 8u * (2 * NX + 2 * NG + g); };
   auto acc2full = [&](int g) { return base + 8u * (2 * NX + 3 * NG + g); };
   auto acc2empty = [&](int g) { return base + 8u * (2 * NX + 4 * NG + g); };
-  const uint32_t tmem_slot = base + 8u * (2 * NX + 5 * NG);
+  auto wfull = [&](int s) { return base + 8u * (2 * NX + 5 * NG + s); };
+  auto wempty = [&](int s) { return base + 8u * (2 * NX + 5 * NG + Cfg::NW + s); };
+  const uint32_t tmem_slot = base + 8u * (2 * NX + 5 * NG + 2 * Cfg::NW);
   const uint32_t sbias = base + Cfg::OFF_BIAS;   // b7[C], b1[C]
   const uint32_t sW7 = base + Cfg::OFF_W7, sW1 = base + Cfg::OFF_W1, sX = base + Cfg::OFF_X, sT = base + Cfg::OFF_T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,6 +130,7 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
       mbar_init(acc1full(g), 1); mbar_init(acc1empty(g), 4); mbar_init(tfull(g), 4);
       mbar_init(acc2full(g), 1); mbar_init(acc2empty(g), 4);
     }
+    for (int s2 = 0; s2 < Cfg::NW; ++s2) { mbar_init(wfull(s2), 32); mbar_init(wempty(s2), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -130,7 +138,7 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // resident weights -> panel layout [K/8][cout][16 B]; biases
-  for (int idx = threadIdx.x; idx < C * 7 * P; idx += kRuThreads) {
+  for (int idx = threadIdx.x; idx < (Cfg::STREAM ? 0 : C * 7 * P); idx += kRuThreads) {
     const int co = idx / (7 * P), pn = idx - co * (7 * P);
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.w7 + (size_t)co * 7 * C) + pn);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sW7 + (uint32_t)pn * Cfg::WS + (uint32_t)co * 16u), "r"(v.x), "r"(v.y),
@@ -198,6 +206,7 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
         umma_commit(acc2full(g));
       };
       int it = 0;
+      uint32_t wcount = 0;   // streamed weight chunks consumed so far
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int g = it % NG, s = it % NX;
         const uint32_t n = (uint32_t)(it / NG);
@@ -207,24 +216,58 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(g * 2 * C);
         const uint32_t xa = sX + (uint32_t)s * Cfg::XBYTES;
+        if constexpr (Cfg::STREAM) {
+          // k7 weights arrive chunk by chunk ([C][64 K] = tap j, K half h) through the ring filled by the weight producer warp
 #pragma unroll 1
-        for (int j = 0; j < 7; ++j) {
+          for (int q = 0; q < 7 * (C / 64); ++q, ++wcount) {
+            const int j = q / (C / 64), h = q - j * (C / 64), ws = (int)(wcount % Cfg::NW);
+            mbar_wait(wfull(ws), (wcount / Cfg::NW) & 1u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_after();
+            const uint32_t wb = sW7 + (uint32_t)ws * Cfg::WCH;
 #pragma unroll
-          for (int kk = 0; kk < C / 16; ++kk)
-            umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
-                      make_desc_ns(sW7 + (uint32_t)(j * P + 2 * kk) * Cfg::WS, Cfg::WS), idesc, (j | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(8 * h + 2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
+                        make_desc_ns(wb + (uint32_t)(2 * kk) * Cfg::WS, Cfg::WS), idesc, (q | kk) != 0 ? 1u : 0u);
+            umma_commit(wempty(ws));           // frees the ring stage when these MMAs retire
+          }
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 7; ++j) {
+#pragma unroll
+            for (int kk = 0; kk < C / 16; ++kk)
+              umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
+                        make_desc_ns(sW7 + (uint32_t)(j * P + 2 * kk) * Cfg::WS, Cfg::WS), idesc, (j | kk) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(acc1full(g));
         if (it >= LAG) issue_k1(it - LAG);   // the oldest tile still waiting for its 1x1 conv: its operand is (nearly) ready by now
       }
       for (int j = (it >= LAG ? it - LAG : 0); j < it; ++j) issue_k1(j);
     }
+  } else if (Cfg::STREAM && warp == 2) {
+    // ===================== weight producer (C = 128): k7 weights, one [C][64 K] chunk per ring stage =====================
+    // lanes = 4 out-channels x 8 panels: 128 contiguous bytes of a weight row per 8 lanes; panel stride WS = 2 KB + 16 B
+    const int pn = lane & 7, co0 = lane >> 3;
+    uint32_t wcount = 0;
+    for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+#pragma unroll 1
+      for (int q = 0; q < 7 * (C / 64); ++q, ++wcount) {
+        const int ws = (int)(wcount % Cfg::NW);
+        if (wcount >= (uint32_t)Cfg::NW) mbar_wait(wempty(ws), ((wcount / Cfg::NW) - 1u) & 1u);
+        const __nv_bfloat16* src = a.w7 + (size_t)q * 64 + pn * 8;              // K offset of chunk q = (tap j) * C + h * 64 = 64 q
+        const uint32_t dst = sW7 + (uint32_t)ws * Cfg::WCH + (uint32_t)pn * Cfg::WS;
+#pragma unroll 4
+        for (int co = co0; co < C; co += 4) cp_async16(dst + (uint32_t)co * 16u, src + (size_t)co * 7 * C, 16u);
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(wfull(ws)) : "memory");
+      }
+    }
   } else {
     // ===================== epilogue: group g = tiles with it % NG == g; thread = one row of the tile =====================
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - Cfg::EPI0) >> 2;
     const int r = quarter * 32 + lane;          // row in the tile
-    const int et = (threadIdx.x - 64) & 127;
+    const int et = (threadIdx.x - 32 * Cfg::EPI0) & 127;
     const uint32_t tg = sT + (uint32_t)g * Cfg::TBYTES;
     int it = 0;
     for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {

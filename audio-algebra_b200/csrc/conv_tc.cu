@@ -655,7 +655,8 @@ struct TcState {
   std::vector<LayerPlan> plans;
   bool weights_valid = false;
   int max_smem = 0;
-  bool fuse_ru = true;          // ResidualUnits with C = 32 / 64 run as one fused kernel (conv_ru.cuh)
+  bool fuse_ru = true;          // ResidualUnits with C = 32 / 64 / 128 run as one fused kernel (conv_ru.cuh)
+  bool fuse_ru128 = false;
   int ru_ctas_per_sm[2] = {1, 1};
 };
 
@@ -709,6 +710,11 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<32>::SMEM));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<64>::SMEM));
+  AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuCfg<128>::SMEM));
+  // C = 128 units: the fused kernel is correct but measured SLOWER than the two layer-wise kernels (420 vs 232 us at B=64): 229 KB of
+  // k7 weights per 128-position tile must stream through a 2-stage ring (all the shared memory left), too shallow for the L2
+  // latency.  Off by default; AA_RU128=1 enables it (tests, and the 2-CTA multicast follow-up).
+  st->fuse_ru128 = getenv("AA_RU128") != nullptr;
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   AA_CUDA(cudaFuncSetAttribute(ru_fused_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   AA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->ru_ctas_per_sm[0], ru_fused_kernel<32>, RuCfg<32>::THREADS, RuCfg<32>::SMEM));
@@ -808,7 +814,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     while (dst == cur || dst == res_buf) ++dst;
     // ---- fused ResidualUnit: k7 (dilated) conv -> ELU -> 1x1 conv -> + x -> ELU in one kernel (conv_ru.cuh) ----
     if (st->fuse_ru && ly.role == ROLE_RES_FIRST && i + 2 < layers.size() && layers[i + 1].role == ROLE_RES_SECOND && ly.k == 7 &&
-        ly.stride == 1 && ly.cin == ly.cout && (ly.cin == 32 || ly.cin == 64) && ly.pad == 3 * ly.dil && ly.dil <= 9 && ly.elu &&
+        ly.stride == 1 && ly.cin == ly.cout && (ly.cin == 32 || ly.cin == 64 || (ly.cin == 128 && st->fuse_ru128)) && ly.pad == 3 * ly.dil && ly.dil <= 9 && ly.elu &&
         layers[i + 1].k == 1 && layers[i + 1].stride == 1 && layers[i + 1].cin == ly.cin && layers[i + 1].cout == ly.cin &&
         layers[i + 1].elu && lout == l) {
       RuArgs ra{};
@@ -820,9 +826,12 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
       if (ly.cin == 32) {
         const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms() * st->ru_ctas_per_sm[0]);
         ru_fused_kernel<32><<<grid, RuCfg<32>::THREADS, RuCfg<32>::SMEM, stream>>>(ra);
-      } else {
+      } else if (ly.cin == 64) {
         const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms() * st->ru_ctas_per_sm[1]);
         ru_fused_kernel<64><<<grid, RuCfg<64>::THREADS, RuCfg<64>::SMEM, stream>>>(ra);
+      } else {
+        const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms());
+        ru_fused_kernel<128><<<grid, RuCfg<128>::THREADS, RuCfg<128>::SMEM, stream>>>(ra);
       }
       AA_LAUNCH_CHECK();
       cur = dst;

@@ -130,11 +130,17 @@ def test_bf16_fused_residual_units_match_layerwise(setup):
         return w
 
     fused, layerwise = make(False), make(True)
+    os.environ["AA_RU128"] = "1"          # also fuse the C = 128 units (streamed k7 weights; off by default: slower)
+    try:
+        fused128 = make(False)
+    finally:
+        os.environ.pop("AA_RU128", None)
     for shape, seed in [((2, 2, 16384), 21), ((3, 2, 5000), 22), ((1, 2, 131072), 23), ((5, 2, 640), 24), ((1, 2, 128), 25)]:
         x = _x(shape, seed).cuda()
-        a, b = fused.encode(x), layerwise.encode(x)
-        assert tuple(a.shape) == tuple(b.shape)
+        a, b, c = fused.encode(x), layerwise.encode(x), fused128.encode(x)
+        assert tuple(a.shape) == tuple(b.shape) == tuple(c.shape)
         assert rel_l2(a, b.cpu()) < 1.5e-2, (shape, rel_l2(a, b.cpu()))
+        assert rel_l2(c, b.cpu()) < 1.5e-2, (shape, rel_l2(c, b.cpu()))
 
 
 def test_fused_fader_mix_three_and_four_stems(setup):
