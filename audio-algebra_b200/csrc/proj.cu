@@ -12,6 +12,7 @@
 // forward), back-propagates, and accumulates the weight / bias gradients per CTA; a second kernel sums
 // the per-CTA partials in a fixed order (deterministic).
 #include "aa_common.cuh"
+#include "packed_f32x2.cuh"
 
 #include <algorithm>
 
@@ -19,8 +20,9 @@ namespace {
 
 constexpr int PD = 64;        // padded feature dim
 constexpr int TT = 32;        // tokens per tile
+constexpr int TSD = TT + 4;   // row stride of the activation tiles: 16-byte aligned rows, and 16 consecutive feature rows hit distinct bank groups
 constexpr int PTHREADS = 256; // 16 x 16 threads, 4 (features) x 2 (tokens) micro tile
-constexpr int WLD = PD + 1;   // padded leading dim of weight tiles in smem (W[o][i])
+constexpr int WLD = PD + 4;   // padded leading dim of weight tiles in smem (W[o][i]): rows stay 16-byte aligned for float4 loads
 
 struct ProjArgs {
   const float* w[4];
@@ -59,32 +61,38 @@ template <bool ACT, bool STORE_U>
 __device__ __forceinline__ void layer_fwd(const float* __restrict__ sW, const float* __restrict__ sB, const float* __restrict__ Hin,
                                           float* __restrict__ Hout, float* __restrict__ U, bool resid) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][2];
+  float2 acc[4];   // the two tokens of the micro tile ride in one packed fp32x2 accumulator (FFMA2: one issue slot per 2 FMAs)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i][0] = sB[ty * 4 + i]; acc[i][1] = acc[i][0]; }
-#pragma unroll 8
-  for (int k = 0; k < PD; ++k) {
-    const float2 h = *reinterpret_cast<const float2*>(Hin + k * TT + tx * 2);
+  for (int i = 0; i < 4; ++i) acc[i] = make_float2(sB[ty * 4 + i], sB[ty * 4 + i]);
+  // four input features per step: one float4 of weights per output feature (broadcast within the half-warp that shares ty)
+  // and one float2 of activations per input feature -> 8 shared loads per 32 FMAs
+#pragma unroll 4
+  for (int k = 0; k < PD; k += 4) {
+    float2 h[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) h[kk] = *reinterpret_cast<const float2*>(Hin + (k + kk) * TSD + tx * 2);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float w = sW[(ty * 4 + i) * WLD + k];
-      acc[i][0] = fmaf(w, h.x, acc[i][0]);
-      acc[i][1] = fmaf(w, h.y, acc[i][1]);
+      const float4 w = *reinterpret_cast<const float4*>(sW + (ty * 4 + i) * WLD + k);
+      acc[i] = pfma(h[0], w.x, acc[i]);
+      acc[i] = pfma(h[1], w.y, acc[i]);
+      acc[i] = pfma(h[2], w.z, acc[i]);
+      acc[i] = pfma(h[3], w.w, acc[i]);
     }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int o = ty * 4 + i;
     float2 r;
-    if (STORE_U) *reinterpret_cast<float2*>(U + o * TT + tx * 2) = make_float2(acc[i][0], acc[i][1]);
-    r.x = ACT ? gelu_erf(acc[i][0]) : acc[i][0];
-    r.y = ACT ? gelu_erf(acc[i][1]) : acc[i][1];
+    if (STORE_U) *reinterpret_cast<float2*>(U + o * TSD + tx * 2) = acc[i];
+    r.x = ACT ? gelu_erf(acc[i].x) : acc[i].x;
+    r.y = ACT ? gelu_erf(acc[i].y) : acc[i].y;
     if (resid) {
-      const float2 h = *reinterpret_cast<const float2*>(Hin + o * TT + tx * 2);
+      const float2 h = *reinterpret_cast<const float2*>(Hin + o * TSD + tx * 2);
       r.x += h.x;
       r.y += h.y;
     }
-    *reinterpret_cast<float2*>(Hout + o * TT + tx * 2) = r;
+    *reinterpret_cast<float2*>(Hout + o * TSD + tx * 2) = r;
   }
 }
 
@@ -95,7 +103,7 @@ __device__ __forceinline__ void load_tile(const ProjArgs& a, const float* __rest
   t0 = (int)(tile % tiles_t) * TT;
   for (int e = threadIdx.x; e < PD * TT; e += blockDim.x) {
     const int c = e / TT, tt = e % TT;
-    H[e] = (c < a.dims && t0 + tt < a.t) ? src[((long long)bi * a.dims + c) * a.t + t0 + tt] : 0.f;
+    H[c * TSD + tt] = (c < a.dims && t0 + tt < a.t) ? src[((long long)bi * a.dims + c) * a.t + t0 + tt] : 0.f;
   }
 }
 
@@ -103,9 +111,9 @@ __global__ void __launch_bounds__(PTHREADS) proj_fwd_kernel(const ProjArgs a) {
   extern __shared__ float sm[];
   float* sW = sm;                      // [4][PD][WLD]
   float* sB = sW + 4 * PD * WLD;       // [4][PD]
-  float* H0 = sB + 4 * PD;             // [PD][TT] tile of x
-  float* Ha = H0 + PD * TT;
-  float* Hb = Ha + PD * TT;
+  float* H0 = sB + 4 * PD;             // [PD][TSD] tile of x
+  float* Ha = H0 + PD * TSD;
+  float* Hb = Ha + PD * TSD;
   load_weights(a, sW, sB);
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     int bi, t0;
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(PTHREADS) proj_fwd_kernel(const ProjArgs a) {
     for (int e = threadIdx.x; e < PD * TT; e += blockDim.x) {
       const int c = e / TT, tt = e % TT;
       if (c < a.dims && t0 + tt < a.t)
-        a.out[((long long)bi * a.dims + c) * a.t + t0 + tt] = Hb[e] + (a.resid_outer ? H0[e] : 0.f);
+        a.out[((long long)bi * a.dims + c) * a.t + t0 + tt] = Hb[c * TSD + tt] + (a.resid_outer ? H0[c * TSD + tt] : 0.f);
     }
   }
 }
@@ -140,44 +148,52 @@ struct ProjBwdArgs {
 __device__ __forceinline__ void layer_bwd_data(const float* __restrict__ sW, const float* __restrict__ dU,
                                                const float* __restrict__ dHout, float* __restrict__ dHin, bool resid) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][2] = {};
+  float2 acc[4] = {};
 #pragma unroll 8
   for (int o = 0; o < PD; ++o) {
-    const float2 g = *reinterpret_cast<const float2*>(dU + o * TT + tx * 2);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float w = sW[o * WLD + ty * 4 + i];
-      acc[i][0] = fmaf(w, g.x, acc[i][0]);
-      acc[i][1] = fmaf(w, g.y, acc[i][1]);
-    }
+    const float2 g = *reinterpret_cast<const float2*>(dU + o * TSD + tx * 2);
+    const float4 w = *reinterpret_cast<const float4*>(sW + o * WLD + ty * 4);   // W[o][i .. i+3]
+    acc[0] = pfma(g, w.x, acc[0]);
+    acc[1] = pfma(g, w.y, acc[1]);
+    acc[2] = pfma(g, w.z, acc[2]);
+    acc[3] = pfma(g, w.w, acc[3]);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = ty * 4 + i;
-    float2 r = make_float2(acc[i][0], acc[i][1]);
+    float2 r = acc[i];
     if (resid) {
-      const float2 h = *reinterpret_cast<const float2*>(dHout + c * TT + tx * 2);
+      const float2 h = *reinterpret_cast<const float2*>(dHout + c * TSD + tx * 2);
       r.x += h.x;
       r.y += h.y;
     }
-    *reinterpret_cast<float2*>(dHin + c * TT + tx * 2) = r;
+    *reinterpret_cast<float2*>(dHin + c * TSD + tx * 2) = r;
   }
 }
 
-// gW[o][i] += sum_t dU[o][t] Hin[i][t]; thread (ty,tx): o = ty*4.., i = tx*4..   (registers, persistent over tiles)
+// gW[o][i] += sum_t dU[o][t] Hin[i][t]; thread (ty,tx): o = ty*4 + a, i = tx + 16 b   (registers, persistent over tiles).
+// The 16 lanes of a half-warp read 16 consecutive feature rows (stride TSD = 36 floats -> distinct 16-byte bank groups).
 __device__ __forceinline__ void layer_bwd_weight(const float* __restrict__ dU, const float* __restrict__ Hin, float (&gw)[4][4],
                                                  float (&gb)[4]) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-#pragma unroll 4
-  for (int t = 0; t < TT; ++t) {
-    float du[4], h[4];
+#pragma unroll 2
+  for (int t = 0; t < TT; t += 4) {      // four tokens per step: 8 float4 loads per 64 FMAs
+    float4 du[4], h[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { du[e] = dU[(ty * 4 + e) * TT + t]; h[e] = Hin[(tx * 4 + e) * TT + t]; }
+    for (int e = 0; e < 4; ++e) {
+      du[e] = *reinterpret_cast<const float4*>(dU + (ty * 4 + e) * TSD + t);
+      h[e] = *reinterpret_cast<const float4*>(Hin + (tx + 16 * e) * TSD + t);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) gw[i][j] = fmaf(du[i], h[j], gw[i][j]);
-      if (tx == 0) gb[i] += du[i];
+      for (int j = 0; j < 4; ++j) {
+        gw[i][j] = fmaf(du[i].x, h[j].x, gw[i][j]);
+        gw[i][j] = fmaf(du[i].y, h[j].y, gw[i][j]);
+        gw[i][j] = fmaf(du[i].z, h[j].z, gw[i][j]);
+        gw[i][j] = fmaf(du[i].w, h[j].w, gw[i][j]);
+      }
+      if (tx == 0) gb[i] += (du[i].x + du[i].y) + (du[i].z + du[i].w);
     }
   }
 }
@@ -187,12 +203,13 @@ __global__ void __launch_bounds__(PTHREADS) proj_bwd_kernel(const ProjBwdArgs ba
   extern __shared__ float sm[];
   float* sW = sm;                      // [4][PD][WLD]
   float* sB = sW + 4 * PD * WLD;       // [4][PD]
-  float* H = sB + 4 * PD;              // H[0..3]: inputs of the four layers, [PD][TT] each
-  float* U = H + 4 * PD * TT;          // U[0..2]: pre-activations of the GELU layers
-  float* G = U + 3 * PD * TT;          // dL/dout tile (kept for the outer residual)
-  float* GA = G + PD * TT;             // gradient ping
-  float* GB = GA + PD * TT;            // gradient pong
-  float* DU = GB + PD * TT;            // dL/dU of the current layer
+  constexpr int TILE = PD * TSD;
+  float* H = sB + 4 * PD;              // H[0..3]: inputs of the four layers, [PD][TSD] each
+  float* U = H + 4 * TILE;             // U[0..2]: pre-activations of the GELU layers
+  float* G = U + 3 * TILE;             // dL/dout tile (kept for the outer residual)
+  float* GA = G + TILE;                // gradient ping
+  float* GB = GA + TILE;               // gradient pong
+  float* DU = GB + TILE;               // dL/dU of the current layer
   load_weights(a, sW, sB);
   float gw[4][4][4] = {};
   float gb[4][4] = {};
@@ -203,23 +220,26 @@ __global__ void __launch_bounds__(PTHREADS) proj_bwd_kernel(const ProjBwdArgs ba
     load_tile(a, ba.gout, tile, G, bi, t0);
     __syncthreads();
     // forward recompute: inputs of every layer and the pre-activations of the GELU layers
-    layer_fwd<true, true>(sW, sB, H, H + PD * TT, U, a.resid_inner[0]);
+    layer_fwd<true, true>(sW, sB, H, H + TILE, U, a.resid_inner[0]);
     __syncthreads();
-    layer_fwd<true, true>(sW + PD * WLD, sB + PD, H + PD * TT, H + 2 * PD * TT, U + PD * TT, a.resid_inner[1]);
+    layer_fwd<true, true>(sW + PD * WLD, sB + PD, H + TILE, H + 2 * TILE, U + TILE, a.resid_inner[1]);
     __syncthreads();
-    layer_fwd<true, true>(sW + 2 * PD * WLD, sB + 2 * PD, H + 2 * PD * TT, H + 3 * PD * TT, U + 2 * PD * TT, a.resid_inner[2]);
+    layer_fwd<true, true>(sW + 2 * PD * WLD, sB + 2 * PD, H + 2 * TILE, H + 3 * TILE, U + 2 * TILE, a.resid_inner[2]);
     __syncthreads();
     // layer 3 (no activation): dU3 = dH4 = gout
-    layer_bwd_weight(G, H + 3 * PD * TT, gw[3], gb[3]);
+    layer_bwd_weight(G, H + 3 * TILE, gw[3], gb[3]);
     layer_bwd_data(sW + 3 * PD * WLD, G, G, GA, a.resid_inner[3]);   // GA = dH3
     __syncthreads();
     float* gin = GA;
     float* gnext = GB;
 #pragma unroll
     for (int l = 2; l >= 0; --l) {
-      for (int e = threadIdx.x; e < PD * TT; e += blockDim.x) DU[e] = gin[e] * gelu_erf_grad(U[l * PD * TT + e]);
+      for (int e = threadIdx.x; e < PD * TT; e += blockDim.x) {
+        const int idx = (e / TT) * TSD + (e % TT);
+        DU[idx] = gin[idx] * gelu_erf_grad(U[l * TILE + idx]);
+      }
       __syncthreads();
-      layer_bwd_weight(DU, H + l * PD * TT, gw[l], gb[l]);
+      layer_bwd_weight(DU, H + l * TILE, gw[l], gb[l]);
       layer_bwd_data(sW + l * PD * WLD, DU, gin, gnext, a.resid_inner[l]);   // gnext = dH_l
       __syncthreads();
       float* tmp = gin; gin = gnext; gnext = tmp;
@@ -230,7 +250,7 @@ __global__ void __launch_bounds__(PTHREADS) proj_bwd_kernel(const ProjBwdArgs ba
         const int c = e / TT, tt = e % TT;
         if (c < a.dims && t0 + tt < a.t) {
           const long long o = ((long long)bi * a.dims + c) * a.t + t0 + tt;
-          const float g = gin[e] + (a.resid_outer ? G[e] : 0.f);
+          const float g = gin[c * TSD + tt] + (a.resid_outer ? G[c * TSD + tt] : 0.f);
           ba.gx[o] = ba.accumulate_gx ? ba.gx[o] + g : g;
         }
       }
@@ -243,7 +263,7 @@ __global__ void __launch_bounds__(PTHREADS) proj_bwd_kernel(const ProjBwdArgs ba
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) p[l * (PD * PD + PD) + (ty * 4 + i) * PD + tx * 4 + j] = gw[l][i][j];
+      for (int j = 0; j < 4; ++j) p[l * (PD * PD + PD) + (ty * 4 + i) * PD + tx + 16 * j] = gw[l][i][j];
       if (tx == 0) p[l * (PD * PD + PD) + PD * PD + ty * 4 + i] = gb[l][i];
     }
   }
@@ -300,8 +320,8 @@ int fill_args(ProjArgs& a, const float* const* w, const float* const* b, int dim
   return AA_OK;
 }
 
-constexpr int kFwdSmem = (4 * PD * WLD + 4 * PD + 3 * PD * TT) * 4;
-constexpr int kBwdSmem = (4 * PD * WLD + 4 * PD + (4 + 3 + 4) * PD * TT) * 4;
+constexpr int kFwdSmem = (4 * PD * WLD + 4 * PD + 3 * PD * TSD) * 4;
+constexpr int kBwdSmem = (4 * PD * WLD + 4 * PD + (4 + 3 + 4) * PD * TSD) * 4;
 
 }  // namespace
 
