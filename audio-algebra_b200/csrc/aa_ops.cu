@@ -176,26 +176,53 @@ __global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------ variance loss
-// One thread per feature column d: Welford over the batch (coalesced across threads).
-__global__ void var_stats_kernel(const float* __restrict__ z, int b, long long d, float gamma, float eps, int hinge_l2,
-                                 float* __restrict__ stats, float* __restrict__ parts) {
+// A block owns 32 feature columns (lane = column, coalesced 128-byte rows); its 8 warps split the batch into 8 contiguous slices.  Every slice accumulates sum and sum of squares of (v - shift) with the column's first sample
+// as shift (4 independent chains: the loop is bandwidth bound, not latency bound like a per-sample Welford update); the slices
+// are merged in a fixed order, so the result is deterministic.  mean = shift + S/n, M2 = Q - S^2/n.
+__global__ void __launch_bounds__(kRedThreads) var_stats_kernel(const float* __restrict__ z, int b, long long d, float gamma, float eps,
+                                                                int hinge_l2, float* __restrict__ stats, float* __restrict__ parts) {
   __shared__ float sh[32];
-  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  float h = 0.f;
-  if (col < d) {
-    float mean = 0.f, m2 = 0.f;
-    for (int i = 0; i < b; ++i) {
-      const float v = z[(long long)i * d + col];
-      const float dl = v - mean;
-      mean += dl / (float)(i + 1);
-      m2 = fmaf(dl, v - mean, m2);
+  __shared__ float sS[8][32], sQ[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i0 = (int)(((long long)b * w) / 8), i1 = (int)(((long long)b * (w + 1)) / 8);
+  float hsum = 0.f;
+  {
+    const long long col = blockIdx.x * 32LL + lane;
+    const bool ok = col < d;
+    const float* p = z + (ok ? col : 0);
+    const float shift = ok ? __ldg(p) : 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    int i = i0;
+    if (ok) {
+#pragma unroll 2
+      for (; i + 3 < i1; i += 4) {
+        const float v0 = __ldg(p + (long long)i * d) - shift, v1 = __ldg(p + (long long)(i + 1) * d) - shift;
+        const float v2 = __ldg(p + (long long)(i + 2) * d) - shift, v3 = __ldg(p + (long long)(i + 3) * d) - shift;
+        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1); q2 = fmaf(v2, v2, q2); q3 = fmaf(v3, v3, q3);
+      }
+      for (; i < i1; ++i) {
+        const float v0 = __ldg(p + (long long)i * d) - shift;
+        s0 += v0; q0 = fmaf(v0, v0, q0);
+      }
     }
-    const float var = (b > 1) ? m2 / (float)(b - 1) : 0.f;
-    if (stats) { stats[col] = mean; stats[d + col] = var; }
-    const float r = fmaxf(gamma - sqrtf(var + eps), 0.f);
-    h = hinge_l2 ? r * r : r;
+    sS[w][lane] = (s0 + s1) + (s2 + s3);
+    sQ[w][lane] = (q0 + q1) + (q2 + q3);
+    __syncthreads();
+    if (w == 0 && ok) {
+      float S = 0.f, Q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { S += sS[k][lane]; Q += sQ[k][lane]; }
+      const float mean_s = S / (float)b;
+      const float m2 = fmaxf(Q - S * mean_s, 0.f);
+      const float var = (b > 1) ? m2 / (float)(b - 1) : 0.f;
+      if (stats) { stats[col] = shift + mean_s; stats[d + col] = var; }
+      const float r = fmaxf(gamma - sqrtf(var + eps), 0.f);
+      hsum += hinge_l2 ? r * r : r;
+    }
+    __syncthreads();
   }
-  h = block_sum(h, sh);
+  const float h = block_sum(hsum, sh);
   if (parts && threadIdx.x == 0) parts[blockIdx.x] = h;
 }
 __global__ void var_bwd_kernel(const float* __restrict__ z, const float* __restrict__ stats, int b, long long d, float gamma,
@@ -538,7 +565,7 @@ int aa_vicreg_var_fwd_f32(const float* z, int64_t b, int64_t d, float gamma, flo
   AA_REQUIRE(z && workspace, "NULL argument");
   AA_REQUIRE(b >= 2 && d >= 1 && b < (1LL << 31), "need batch >= 2 (unbiased variance), got b=%lld d=%lld", (long long)b, (long long)d);
   cudaStream_t st = (cudaStream_t)stream;
-  const long long blocks = (d + kRedThreads - 1) / kRedThreads;
+  const long long blocks = (d + 31) / 32;
   AA_REQUIRE(blocks <= (1LL << 30), "d too large");
   // partial sums: one per block; more than kMaxParts blocks are folded by the finalizer anyway (any count works)
   float* parts = workspace;
