@@ -621,19 +621,38 @@ __device__ __forceinline__ void fft_regs(float2 (&re)[R], float2 (&im)[R]) {
   }
 }
 
+// Output staging of the warp kernel: a block = 8 warps = 8 CONSECUTIVE frames of one row pair.  Every warp leaves its frame's
+// bins in shared memory (index k + k / R: lanes hold k = k1 + R bitrev5(lane), the skew makes the writes conflict free), then the
+// block stores them with lanes = (4 bins) x (8 frames): 32-byte runs along the frame axis instead of 4-byte scattered stores
+// (the output layout [.., F, T] is frame-minor; see the tile kernel's power epilogue for the same reason).
+template <int R>
+struct WkCfg {
+  static constexpr int M = 32 * R;
+  static constexpr int ROWLEN = ((M + M / (R > 1 ? R : 1) + 8 + 15) / 16) * 16 + 4;   // float2 units; = 4 mod 16: the store pass reads conflict free
+  static constexpr int kThreadsW = 256;
+};
+template <int R>
+__device__ __forceinline__ int wk_idx(int k) { return (R > 1) ? k + k / R : 2 * k; }
+
 template <int R, int MODE>
-__global__ void __launch_bounds__(128) stft_warp_kernel(const StftArgs a, const float2* __restrict__ tw_lane,
-                                                        const float2* __restrict__ tw_split, long long n_items, int mel_w4_count) {
+__global__ void __launch_bounds__(256, 2) stft_warp_kernel(const StftArgs a, const float2* __restrict__ tw_lane,
+                                                           const float2* __restrict__ tw_split, long long n_groups_total, int mel_w4_count) {
   constexpr int M = 32 * R, LOGR = (R == 1) ? 0 : (R == 2) ? 1 : (R == 4) ? 2 : (R == 8) ? 3 : 4;
+  constexpr int ROWLEN = (R > 1) ? WkCfg<R>::ROWLEN : ((2 * M + 8 + 15) / 16) * 16 + 4;
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float2* P = reinterpret_cast<float2*>(smem) + warp * (M + 8);          // mel: this warp's power line (rowA, rowB) per bin
-  // mel: filter tables staged once per (persistent) block: [n_mels] start, [n_mels] count, [n_mels] offset, then the float4 weights
-  int* s_meta = reinterpret_cast<int*>(reinterpret_cast<float2*>(smem) + 4 * (M + 8));
+  // staging: power / mel: SA[8 frames][ROWLEN] float2 (rowA, rowB); complex: SA = real parts, SB = imaginary parts
+  float2* SA = reinterpret_cast<float2*>(smem);
+  float2* SB = SA + 8 * ROWLEN;
+  float2* P = SA + warp * ROWLEN;                                         // this warp's frame line
+  float2* PI = SB + warp * ROWLEN;
+  // mel: results [8 frames][n_mels] float2, then the filter tables staged once per (persistent) block
+  float2* SMEL = SA + 8 * ROWLEN;
+  int* s_meta = reinterpret_cast<int*>(SMEL + 8 * ((a.n_mels + 3) & ~3));
   float4* s_w4 = reinterpret_cast<float4*>(s_meta + ((3 * a.n_mels + 3) & ~3));
   if constexpr (MODE == MODE_MEL) {
-    for (int i = threadIdx.x; i < 3 * a.n_mels; i += 128) s_meta[i] = __ldg(a.mel_start4 + i);   // start | cnt | off are contiguous
-    for (int i = threadIdx.x; i < mel_w4_count; i += 128) s_w4[i] = __ldg(a.mel_w4 + i);
+    for (int i = threadIdx.x; i < 3 * a.n_mels; i += 256) s_meta[i] = __ldg(a.mel_start4 + i);   // start | cnt | off are contiguous
+    for (int i = threadIdx.x; i < mel_w4_count; i += 256) s_w4[i] = __ldg(a.mel_w4 + i);
     __syncthreads();
   }
   // per-lane twiddles of the 5 lane-FFT stages (distance s = 16, 8, 4, 2, 1): upper lanes (lane & s) multiply by W_{2s}^(lane & (s-1))
@@ -653,12 +672,15 @@ __global__ void __launch_bounds__(128) stft_warp_kernel(const StftArgs a, const 
   const bool center = a.center_off != 0;
   const long long n_freq = a.n_freq;
   const bool vec_ok = a.wav_aligned16 && (a.n_in & 1) == 0 && (a.hop & 1) == 0;
+  const int groups_per_pair = (a.n_frames + 7) / 8;
 
-  for (long long item = (long long)blockIdx.x * 4 + warp; item < n_items; item += (long long)gridDim.x * 4) {
-    const long long pair = item / a.n_frames;
-    const int frame = (int)(item - pair * a.n_frames);
+  for (long long grp = blockIdx.x; grp < n_groups_total; grp += gridDim.x) {
+    const long long pair = grp / groups_per_pair;
+    const int f0 = (int)(grp - pair * groups_per_pair) * 8;
+    const int frame = f0 + warp;
     const long long rowA = 2 * pair;
     const bool hasB = rowA + 1 < a.rows;
+    if (frame < a.n_frames) {
     const float* __restrict__ pa = a.wav + rowA * a.n_in;
     const float* __restrict__ pb = hasB ? pa + a.n_in : nullptr;
     const long long s0 = (long long)frame * a.hop - a.center_off;
@@ -713,7 +735,6 @@ __global__ void __launch_bounds__(128) stft_warp_kernel(const StftArgs a, const 
       }
     }
     // lane holds Z[k1 + R k2], k2 = bitrev5(lane).  Real-FFT split: 2 X[k] = (Z[k] + conj Z[M-k]) - i W_{2M}^k (Z[k] - conj Z[M-k])
-    float* outA = a.out;
 #pragma unroll
     for (int k1 = 0; k1 < R; ++k1) {
       const int kp = (k1 == 0) ? 0 : R - k1;                 // partner register
@@ -734,34 +755,19 @@ __global__ void __launch_bounds__(128) stft_warp_kernel(const StftArgs a, const 
       float2 xi = pmuls(pfma(o_r, tw.y, pfma(o_i, tw.x, e_i)), 0.5f);
       if (k == 0) { xr = padd(ar, ai); xi = make_float2(0.f, 0.f); }   // DC
       if constexpr (MODE == MODE_COMPLEX) {
-        float2* o = reinterpret_cast<float2*>(outA) + (rowA * n_freq + k) * a.n_frames + frame;
-        o[0] = make_float2(xr.x, xi.x);
-        if (hasB) o[n_freq * a.n_frames] = make_float2(xr.y, xi.y);
+        P[wk_idx<R>(k)] = xr;
+        PI[wk_idx<R>(k)] = xi;
       } else {
-        const float2 pw = pfma2(xi, xi, pmul(xr, xr));
-        if constexpr (MODE == MODE_POWER) {
-          float* o = outA + (rowA * n_freq + k) * a.n_frames + frame;
-          o[0] = pw.x;
-          if (hasB) o[n_freq * a.n_frames] = pw.y;
-        } else {
-          P[k] = pw;
-        }
+        P[wk_idx<R>(k)] = pfma2(xi, xi, pmul(xr, xr));
       }
     }
     if (lane == 0) {   // Nyquist bin M = Re Z[0] - Im Z[0] (lane 0 holds k2 = 0)
       const float2 ny = psub(re[0], im[0]);
       if constexpr (MODE == MODE_COMPLEX) {
-        float2* o = reinterpret_cast<float2*>(outA) + (rowA * n_freq + M) * a.n_frames + frame;
-        o[0] = make_float2(ny.x, 0.f);
-        if (hasB) o[n_freq * a.n_frames] = make_float2(ny.y, 0.f);
-      } else if constexpr (MODE == MODE_POWER) {
-        float* o = outA + (rowA * n_freq + M) * a.n_frames + frame;
-        o[0] = ny.x * ny.x;
-        if (hasB) o[n_freq * a.n_frames] = ny.y * ny.y;
+        P[wk_idx<R>(M)] = ny;
+        PI[wk_idx<R>(M)] = make_float2(0.f, 0.f);
       } else {
-        P[M] = pmul(ny, ny);
-#pragma unroll
-        for (int j = 1; j < 8; ++j) P[M + j] = make_float2(0.f, 0.f);
+        P[wk_idx<R>(M)] = pmul(ny, ny);
       }
     }
     if constexpr (MODE == MODE_MEL) {
@@ -772,16 +778,46 @@ __global__ void __launch_bounds__(128) stft_warp_kernel(const StftArgs a, const 
         float2 acc = make_float2(0.f, 0.f);
         for (int j = 0; j < cnt; ++j) {
           const float4 w = w4[j];
-          const float2* pp = P + start + 4 * j;
-          acc = pfma(pp[0], w.x, acc); acc = pfma(pp[1], w.y, acc);
-          acc = pfma(pp[2], w.z, acc); acc = pfma(pp[3], w.w, acc);
+          const int kb = start + 4 * j;
+          if (kb <= M) acc = pfma(P[wk_idx<R>(kb)], w.x, acc);
+          if (kb + 1 <= M) acc = pfma(P[wk_idx<R>(kb + 1)], w.y, acc);
+          if (kb + 2 <= M) acc = pfma(P[wk_idx<R>(kb + 2)], w.z, acc);
+          if (kb + 3 <= M) acc = pfma(P[wk_idx<R>(kb + 3)], w.w, acc);
         }
-        float* o = outA + (rowA * a.n_mels + m) * a.n_frames + frame;
-        o[0] = 4.0f * acc.x;
-        if (hasB) o[(long long)a.n_mels * a.n_frames] = 4.0f * acc.y;
+        SMEL[warp * ((a.n_mels + 3) & ~3) + m] = pmuls(acc, 4.0f);
       }
-      __syncwarp();
     }
+    }   // frame < n_frames
+    __syncthreads();
+    // ---- block store: lanes = (4 bins / filters) x (8 frames): 32-byte runs along the frame axis ----
+    {
+      const int f = threadIdx.x & 7, kb = threadIdx.x >> 3;
+      const bool fok = f0 + f < a.n_frames;
+      if constexpr (MODE == MODE_MEL) {
+        const int mstride = (a.n_mels + 3) & ~3;
+        float* o = a.out + (rowA * a.n_mels) * a.n_frames + f0 + f;
+        for (int m = kb; m < a.n_mels && fok; m += 32) {
+          const float2 v = SMEL[f * mstride + m];
+          o[(long long)m * a.n_frames] = v.x;
+          if (hasB) o[((long long)a.n_mels + m) * a.n_frames] = v.y;
+        }
+      } else if constexpr (MODE == MODE_POWER) {
+        float* o = a.out + (rowA * n_freq) * a.n_frames + f0 + f;
+        for (int k = kb; k <= M && fok; k += 32) {
+          const float2 v = SA[f * ROWLEN + wk_idx<R>(k)];
+          o[(long long)k * a.n_frames] = v.x;
+          if (hasB) o[(n_freq + k) * a.n_frames] = v.y;
+        }
+      } else {
+        float2* o = reinterpret_cast<float2*>(a.out) + (rowA * n_freq) * a.n_frames + f0 + f;
+        for (int k = kb; k <= M && fok; k += 32) {
+          const float2 vr = SA[f * ROWLEN + wk_idx<R>(k)], vi = SB[f * ROWLEN + wk_idx<R>(k)];
+          o[(long long)k * a.n_frames] = make_float2(vr.x, vi.x);
+          if (hasB) o[(n_freq + k) * a.n_frames] = make_float2(vr.y, vi.y);
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1100,18 +1136,31 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
     a.mel_hdr_bytes = a.mel_w_bytes = 0; a.lane_consts = nullptr;
     if (p->wk_r > 0) {
       const int R = p->wk_r;
-      const long long n_items = ((rows + 1) / 2) * n_frames;
-      const unsigned wgrid = (unsigned)std::min<long long>((n_items + 3) / 4, (long long)aa::num_sms() * 16);
-      const int wsmem = (mode == MODE_MEL) ? 4 * (32 * R + 8) * 8 + ((3 * p->n_mels + 3) & ~3) * 4 + p->mel_w4_count * 16 : 0;
-      AA_REQUIRE(wsmem <= 48 * 1024, "mel filterbank too large for the warp STFT kernel (%d bytes)", wsmem);
+      const long long n_groups = ((rows + 1) / 2) * ((n_frames + 7) / 8);
+      const unsigned wgrid = (unsigned)std::min<long long>(n_groups, (long long)aa::num_sms() * 8);
+      const int M_ = 32 * R;
+      const int rowlen = (R > 1) ? ((M_ + M_ / R + 8 + 15) / 16) * 16 + 4 : ((2 * M_ + 8 + 15) / 16) * 16 + 4;
+      const int mstride = (p->n_mels + 3) & ~3;
+      const int wsmem = (mode == MODE_COMPLEX) ? 2 * 8 * rowlen * 8
+                        : (mode == MODE_POWER) ? 8 * rowlen * 8
+                                               : 8 * rowlen * 8 + 8 * mstride * 8 + ((3 * p->n_mels + 3) & ~3) * 4 + p->mel_w4_count * 16;
       const int w4c = p->mel_w4_count;
+      const long long n_items = n_groups;
       const float2* twl = p->d_wk;
       const float2* tws = p->d_wk + (size_t)R * 32;
+      AA_REQUIRE(wsmem <= 200 * 1024, "filterbank too large for the warp STFT kernel (%d bytes of shared memory)", wsmem);
 #define AA_WK(RR)                                                                                                        \
   do {                                                                                                                   \
-    if (mode == MODE_COMPLEX) stft_warp_kernel<RR, MODE_COMPLEX><<<wgrid, 128, wsmem, st>>>(a, twl, tws, n_items, w4c);  \
-    else if (mode == MODE_POWER) stft_warp_kernel<RR, MODE_POWER><<<wgrid, 128, wsmem, st>>>(a, twl, tws, n_items, w4c); \
-    else stft_warp_kernel<RR, MODE_MEL><<<wgrid, 128, wsmem, st>>>(a, twl, tws, n_items, w4c);                          \
+    if (mode == MODE_COMPLEX) {                                                                                          \
+      AA_CUDA(cudaFuncSetAttribute(stft_warp_kernel<RR, MODE_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem)); \
+      stft_warp_kernel<RR, MODE_COMPLEX><<<wgrid, 256, wsmem, st>>>(a, twl, tws, n_items, w4c);                          \
+    } else if (mode == MODE_POWER) {                                                                                     \
+      AA_CUDA(cudaFuncSetAttribute(stft_warp_kernel<RR, MODE_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem));   \
+      stft_warp_kernel<RR, MODE_POWER><<<wgrid, 256, wsmem, st>>>(a, twl, tws, n_items, w4c);                            \
+    } else {                                                                                                             \
+      AA_CUDA(cudaFuncSetAttribute(stft_warp_kernel<RR, MODE_MEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem));     \
+      stft_warp_kernel<RR, MODE_MEL><<<wgrid, 256, wsmem, st>>>(a, twl, tws, n_items, w4c);                              \
+    }                                                                                                                    \
   } while (0)
       if (R == 1) AA_WK(1); else if (R == 2) AA_WK(2); else if (R == 4) AA_WK(4); else if (R == 8) AA_WK(8); else AA_WK(16);
 #undef AA_WK

@@ -169,6 +169,14 @@ def run_extras(dev):
         out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / hbm,
                      "audio_s_per_s": AUDIO_S_PER_STEP / (ms * 1e-3)}
         del res
+    # the reference's own default geometry (n_fft = 1024, hop = 256, given_models.py:259-264) runs on the warp kernel
+    m = aab.MelSpectrogramAE(sample_rate=SR)
+    res = {}
+    ms = timed(lambda: res.__setitem__("o", m.encode(x)), 10)
+    nbytes = x.numel() * 4 + res["o"].numel() * 4
+    out["stft_mel_n1024_h256"] = {"ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / hbm,
+                                  "audio_s_per_s": AUDIO_S_PER_STEP / (ms * 1e-3), "note": "MelSpectrogramAE() reference defaults, stft_warp_kernel"}
+    del res
     del x
     # ---- conv encoder, bf16 tcgen05 path (config 5 encode sweep point): 68.17 GFLOP per 2^17-sample chunk ----
     dvb = aab.DVAEWrapper(debug=False, compute_dtype="bf16").cuda()
