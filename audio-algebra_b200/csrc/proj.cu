@@ -15,6 +15,8 @@
 #include "packed_f32x2.cuh"
 
 #include <algorithm>
+#include <cstdint>
+#include <cstdlib>
 
 namespace {
 
@@ -325,6 +327,10 @@ constexpr int kBwdSmem = (4 * PD * WLD + 4 * PD + (4 + 3 + 4) * PD * TSD) * 4;
 
 }  // namespace
 
+namespace aa {
+int proj_fwd_tc(const float* const* w, const float* const* b, const float* x, int64_t batch, int64_t t, float* out, cudaStream_t stream);
+}
+
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -335,6 +341,13 @@ int aa_projector_half_fwd_f32(const float* const* w_host, const float* const* b_
   if (rc != AA_OK) return rc;
   AA_REQUIRE(out != nullptr, "out is NULL");
   if (a.n_tiles == 0) return AA_OK;
+  // the standard 64 -> 64 residual projector runs on the tensor core (tcgen05, 3-term TF32 split: fp32-accurate, proj_tc.cu);
+  // other shapes (toy dims, no residual, very short sequences) and AA_PROJ_FP32=1 (tests) use the CUDA-core kernel below
+  static const bool force_fp32 = getenv("AA_PROJ_FP32") != nullptr;
+  if (!force_fp32 && dims == PD && hidden == PD && resid && t >= 64 && (reinterpret_cast<uintptr_t>(w_host[0]) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(w_host[1]) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_host[2]) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(w_host[3]) & 15) == 0)
+    return aa::proj_fwd_tc(w_host, b_host, x, batch, t, out, (cudaStream_t)stream);
   static bool attr = false;
   if (!attr) {
     AA_CUDA(cudaFuncSetAttribute(proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));

@@ -277,3 +277,34 @@ def test_adam_matches_torch(aab):
         opt.step(); sched.step()
         mine.step(gr.cuda())
     assert rel_l2(mine.params, pt.detach()) < 1e-6
+
+
+def test_projector_forward_tensor_core_path_is_fp32_accurate(aab):
+    """T' >= 64 with the standard 64 -> 64 residual projector runs the forward on tcgen05 (kind::tf32 with a 3-term hi/lo split,
+    csrc/proj_tc.cu).  Against the float64 oracle it must be as accurate as fp32 arithmetic (the gate is 1e-4; a single-pass
+    TF32 product would sit at ~1e-3), for ragged token counts, both halves, and large-magnitude inputs."""
+    O = _oracle()
+    sd = O.init_projector_state_dict(64, 64, seed=2)
+    aa = aab.AudioAlgebra(64, 64)
+    aa.load_state_dict(sd)
+    aa = aa.cuda()
+    ew, eb, dw, db = O.projector_params_from_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    for shape, scale in [((3, 64, 200), 1.0), ((2, 64, 128), 4.0), ((5, 64, 1024), 0.3), ((1, 64, 64), 1.0), ((2, 64, 65), 1.0)]:
+        y = scale * torch.randn(*shape, generator=g)
+        z, yr = aa(y.cuda())
+        zo, yro = O.projector_forward(y.double(), ew, eb, dw, db)
+        assert rel_l2(z, zo) < 2e-6 and rel_l2(yr, yro) < 2e-6, (shape, rel_l2(z, zo), rel_l2(yr, yro))
+        # elementwise, relative to the tensor's scale: no token / channel may be off (row or panel mix-ups)
+        assert (z.cpu().double() - zo).abs().max().item() < 2e-5 * zo.abs().max().item()
+    # gradients still flow through the (CUDA-core) backward and match the oracle's autograd
+    y = torch.randn(2, 64, 192, generator=g)
+    yc = y.cuda().requires_grad_(True)
+    z, yr = aa(yc)
+    (z.square().mean() + yr.square().mean()).backward()
+    yd = y.double().requires_grad_(True)
+    P = [p.clone().requires_grad_(True) for p in ew + eb + dw + db]
+    zo, yro = O.projector_forward(yd, P[0:4], P[4:8], P[8:12], P[12:16])
+    (zo.square().mean() + yro.square().mean()).backward()
+    assert rel_l2(yc.grad, yd.grad) < 1e-4
+    assert rel_l2(aa.encoder[0].lin.weight.grad, P[0].grad) < 1e-4
