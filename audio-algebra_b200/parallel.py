@@ -5,7 +5,7 @@ flat 33 280-float projector gradient in training and (ii) the sum all-reduce of 
 import torch
 import torch.distributed as dist
 
-__all__ = ['world_info', 'shard_range', 'shard_batch', 'allreduce_mean_', 'allreduce_sum_']
+__all__ = ['world_info', 'shard_range', 'shard_batch', 'allreduce_mean_', 'allreduce_sum_', 'bind_to_gpu_numa_node']
 
 
 def world_info(group=None):
@@ -41,3 +41,30 @@ def allreduce_mean_(t, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         t.div_(world)
     return t
+
+
+def bind_to_gpu_numa_node(device_index):
+    """One process per GPU: restrict this process to the CPUs of the NUMA node its GPU hangs off, so that pinned staging
+    buffers allocated afterwards are first-touched on that node and H2D / D2H copies do not cross the socket interconnect
+    (matters when all 8 ranks of a node stream from host memory at once).  Best effort: returns the CPU list, or None when
+    the topology cannot be read (then nothing is changed)."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None

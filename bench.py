@@ -287,6 +287,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     import audio_algebra_b200 as aab
     from audio_algebra_b200._lib import lib
+    numa_cpus = aab.parallel.bind_to_gpu_numa_node(local) if (world > 1 and not os.environ.get("AA_NO_NUMA_BIND")) else None
 
     def barrier():
         if world > 1:
@@ -351,7 +352,8 @@ def run_ours(args):
                        "l2": "inputs (268 MB per step) exceed the 126 MB L2; no extra flush"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": BATCH * 2 * CHUNK * 4,
                     "d2h_bytes_per_step": BATCH * 2 * N_MELS * (1 + CHUNK // HOP) * 4,
-                    "api": "MelSpectrogramAE.encode(pinned CPU tensor) -> aa_stft_mel_f32_host (chunked, copies overlapped)"},
+                    "api": "MelSpectrogramAE.encode(pinned CPU tensor) -> aa_stft_mel_f32_host (chunked, copies overlapped)",
+                    "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "kernel": "stft2048_kernel<MEL>", "kernel_us": 1e3 * k_ms,
