@@ -9,6 +9,7 @@
 #include "aa_common.cuh"
 
 #include <algorithm>
+#include <cstdint>
 #include <cmath>
 
 namespace {
@@ -379,15 +380,24 @@ __global__ void __launch_bounds__(256) cov_bwd_kernel(const float* __restrict__ 
 // sums[c] over all (b, t) of y[b][c][t]  (one block per (c, slice); fixed-order second stage on host-free path)
 __global__ void chan_sum_part_kernel(const float* __restrict__ y, long long b, int c, long long t, float* __restrict__ parts,
                                      int slices) {
+  // block (ch, slice): the rows y[bi][ch][0..t) of every slices-th batch element, read as contiguous runs (no div / mod per element)
   __shared__ float sh[32];
   const int ch = blockIdx.x, sl = blockIdx.y;
-  float acc = 0.f;
-  const long long n = b * t;
-  for (long long i = sl * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)slices * blockDim.x) {
-    const long long bi = i / t, ti = i % t;
-    acc += y[(bi * c + ch) * t + ti];
+  float acc0 = 0.f, acc1 = 0.f;
+  for (long long bi = sl; bi < b; bi += slices) {
+    const float* row = y + (bi * c + ch) * t;
+    if ((t & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      for (long long i = threadIdx.x; i < t / 4; i += blockDim.x) {
+        const float4 v = __ldg(r4 + i);
+        acc0 += v.x + v.y;
+        acc1 += v.z + v.w;
+      }
+    } else {
+      for (long long i = threadIdx.x; i < t; i += blockDim.x) acc0 += __ldg(row + i);
+    }
   }
-  acc = block_sum(acc, sh);
+  const float acc = block_sum(acc0 + acc1, sh);
   if (threadIdx.x == 0) parts[ch * slices + sl] = acc;
 }
 __global__ void chan_mean_kernel(const float* __restrict__ parts, int c, int slices, double n, float* __restrict__ mean) {
@@ -400,13 +410,15 @@ __global__ void chan_mean_kernel(const float* __restrict__ parts, int c, int sli
 }
 // each block: a run of (b, t-chunk) tiles; 64x64 channel tile of the scatter; writes its partial
 constexpr int PT = 32;   // points per smem tile
+constexpr int PLD = 64 + 4;   // leading dim of the staged [point][channel] tiles: rows stay 16-byte aligned for float4 loads
 __global__ void __launch_bounds__(256) scatter_part_kernel(const float* __restrict__ y, long long b, int c, long long t,
                                                            const float* __restrict__ mean, float* __restrict__ parts) {
-  __shared__ float Ys[PT][64 + 1];
+  __shared__ __align__(16) float Ys[PT][PLD];
+  __shared__ __align__(16) float Yt[PT][PLD];
   const int ci = blockIdx.y, cj = blockIdx.z;   // 64-channel tiles
+  const bool same = (ci == cj);                 // diagonal tile (always, for C <= 64): one staged copy serves both operands
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4] = {};
-  __shared__ float Yt[PT][64 + 1];
   const long long tiles_t = (t + PT - 1) / PT, n_tiles = b * tiles_t;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long bi = tile / tiles_t, t0 = (tile % tiles_t) * PT;
@@ -414,15 +426,16 @@ __global__ void __launch_bounds__(256) scatter_part_kernel(const float* __restri
       const int ch = e / PT, p = e % PT;
       const long long tt = t0 + p;
       const int ca = ci * 64 + ch, cb = cj * 64 + ch;
-      Ys[p][ch] = (tt < t && ca < c) ? y[(bi * c + ca) * t + tt] - mean[ca] : 0.f;
-      Yt[p][ch] = (tt < t && cb < c) ? y[(bi * c + cb) * t + tt] - mean[cb] : 0.f;
+      Ys[p][ch] = (tt < t && ca < c) ? __ldg(y + (bi * c + ca) * t + tt) - mean[ca] : 0.f;
+      if (!same) Yt[p][ch] = (tt < t && cb < c) ? __ldg(y + (bi * c + cb) * t + tt) - mean[cb] : 0.f;
     }
     __syncthreads();
+    const float (*Yb)[PLD] = same ? Ys : Yt;
 #pragma unroll 8
     for (int p = 0; p < PT; ++p) {
-      float av[4], bv[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { av[e] = Ys[p][ty * 4 + e]; bv[e] = Yt[p][tx * 4 + e]; }
+      const float4 a4 = *reinterpret_cast<const float4*>(&Ys[p][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Yb[p][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -439,15 +452,34 @@ __global__ void __launch_bounds__(256) scatter_part_kernel(const float* __restri
       if (r < c && cc < c) p[(long long)r * c + cc] = acc[i][j];
     }
 }
-__global__ void scatter_reduce_kernel(const float* __restrict__ parts, int n_parts, int c, float* __restrict__ cov_num,
-                                      double* __restrict__ count, double n_points) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < c * c) {
+// cov_num[i] += sum_p parts[p][i] in a fixed order: a block owns 32 outputs (lane), its 8 warps split the partials into 8
+// contiguous slices (coalesced 128-byte rows, 4 independent chains), the slices are merged in warp order.
+__global__ void __launch_bounds__(256) scatter_reduce_kernel(const float* __restrict__ parts, int n_parts, int c,
+                                                             float* __restrict__ cov_num, double* __restrict__ count, double n_points) {
+  __shared__ float sS[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane, cc = c * c;
+  const int p0 = (int)(((long long)n_parts * w) / 8), p1 = (int)(((long long)n_parts * (w + 1)) / 8);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < cc) {
+    int p = p0;
+    for (; p + 3 < p1; p += 4) {
+      s0 += __ldg(parts + (long long)p * cc + i);
+      s1 += __ldg(parts + (long long)(p + 1) * cc + i);
+      s2 += __ldg(parts + (long long)(p + 2) * cc + i);
+      s3 += __ldg(parts + (long long)(p + 3) * cc + i);
+    }
+    for (; p < p1; ++p) s0 += __ldg(parts + (long long)p * cc + i);
+  }
+  sS[w][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0 && i < cc) {
     float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += parts[(long long)p * c * c + i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sS[k][lane];
     cov_num[i] += s;
   }
-  if (i == 0 && count) count[0] += n_points;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && count) count[0] += n_points;
 }
 
 // ------------------------------------------------------------------------------------------ Adam
@@ -670,7 +702,7 @@ int aa_cov_accumulate_f32(const float* y, int64_t b, int64_t c, int64_t t, float
   const int blocks = (int)std::min<long long>(n_tiles, std::max(1, scatter_blocks() / (ctiles * ctiles)));
   scatter_part_kernel<<<dim3(blocks, ctiles, ctiles), 256, 0, st>>>(y, b, (int)c, t, mean, parts);
   AA_LAUNCH_CHECK();
-  scatter_reduce_kernel<<<(unsigned)((c * c + 255) / 256), 256, 0, st>>>(parts, blocks, (int)c, cov_num, count,
+  scatter_reduce_kernel<<<(unsigned)((c * c + 31) / 32), 256, 0, st>>>(parts, blocks, (int)c, cov_num, count,
                                                                         (double)b * (double)t);
   AA_LAUNCH_CHECK();
   return AA_OK;
