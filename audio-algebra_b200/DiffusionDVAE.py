@@ -40,7 +40,7 @@ _lib.register({
     "aa_encoder_forward": (_i, [_p, _pp, C.POINTER(_f), _i, _i64, _i64, _i, _i, _p, _p, _p]),
 })
 
-DTYPES = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1}
+DTYPES = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "tf32x3": 2, "3xtf32": 2}
 
 
 class _Handles:

@@ -621,6 +621,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+#include "conv_tf32.cuh"
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -645,6 +647,7 @@ struct LayerPlan {
   int view_s = 1;              // positions per row of the input view
   int k_total = 0;
   __nv_bfloat16* w2 = nullptr;
+  float* w2f = nullptr;        // 3xTF32 path: planes [2][cout][k_total]
 };
 
 }  // namespace
@@ -660,7 +663,7 @@ struct TcState {
   int ru_ctas_per_sm[2] = {1, 1};
 };
 
-static int plan_layer(const ConvLayer& l, LayerPlan& p) {
+static int plan_layer(const ConvLayer& l, LayerPlan& p, bool tf32 = false) {
   p = LayerPlan();
   if (l.stride == 1) {
     p.view_s = 1; p.view_c = l.cin; p.n_taps = l.k;
@@ -674,14 +677,14 @@ static int plan_layer(const ConvLayer& l, LayerPlan& p) {
     p.tap_off[1] = 0;  p.tap_col0[1] = 0;               p.tap_width[1] = s * l.cin;        p.tap_kbase[1] = pd;
     p.tap_off[2] = 1;  p.tap_col0[2] = 0;               p.tap_width[2] = (s - pd) * l.cin; p.tap_kbase[2] = pd + s;
   }
-  p.bk = 64;
+  p.bk = tf32 ? 32 : 64;       // channels per K chunk: 128 bytes of bf16 (64 bytes where a tap is 32 channels wide) or of fp32
   for (int j = 0; j < p.n_taps; ++j) if (p.tap_width[j] % 64 != 0) p.bk = 32;
   p.k_total = 0;
   for (int j = 0; j < p.n_taps; ++j) {
     AA_REQUIRE(p.tap_width[j] % p.bk == 0 && p.tap_col0[j] % p.bk == 0, "channel count %d not a multiple of 32", l.cin);
     p.k_total += p.tap_width[j];
   }
-  AA_REQUIRE(p.k_total / p.bk <= kMaxChunks, "too many K chunks (%d)", p.k_total / p.bk);
+  AA_REQUIRE(p.k_total / p.bk <= (tf32 ? kTfMaxChunks : kMaxChunks), "too many K chunks (%d)", p.k_total / p.bk);
   AA_REQUIRE(l.cout % 32 == 0, "cout=%d must be a multiple of 32 on the tensor-core path", l.cout);
   return AA_OK;
 }
@@ -904,6 +907,176 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     }
     AA_LAUNCH_CHECK();
     if (ly.role == ROLE_RES_SECOND) res_buf = -1;
+    cur = dst;
+    l = lout;
+  }
+  return AA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 3xTF32 path (conv_tf32.cuh): layer-wise, fp32 channels-last activations as hi / lo planes
+// ------------------------------------------------------------------------------------------------------------------
+struct TfState {
+  std::vector<LayerPlan> plans;
+  bool weights_valid = false;
+  int max_smem = 0;
+  int chain = 2;               // K chunks (of 32 channels) per accumulator chain
+};
+
+static int tf_id_cols(const ConvLayer& l) { return l.role == ROLE_RES_SECOND ? l.cout : 0; }
+
+int tf_create(TfState** out, const std::vector<ConvLayer>& layers) {
+  AA_REQUIRE(get_encode_fn() != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  AA_REQUIRE(layers.size() >= 2 && layers[0].stride == 1 && layers[0].cout == 32 && layers[0].cin <= 4 && layers[0].k <= 7,
+             "first layer shape not supported on the 3xTF32 path (needs capacity 32, <= 4 input channels, k <= 7)");
+  TfState* st = new TfState();
+  st->plans.resize(layers.size());
+  for (size_t i = 1; i < layers.size(); ++i) {
+    int rc = plan_layer(layers[i], st->plans[i], true);
+    if (rc != AA_OK) { delete st; return rc; }
+    if (layers[i].role == ROLE_RES_SECOND)
+      AA_REQUIRE(layers[i].cin == layers[i].cout && layers[i].stride == 1, "residual layer %zu must keep its shape", i);
+    AA_CUDA(cudaMalloc(&st->plans[i].w2f, sizeof(float) * 2 * (size_t)layers[i].cout * (st->plans[i].k_total + tf_id_cols(layers[i]))));
+  }
+  int dev = 0;
+  AA_CUDA(cudaGetDevice(&dev));
+  AA_CUDA(cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  AA_CUDA(cudaFuncSetAttribute(conv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  if (getenv("AA_TF32_CHAIN")) st->chain = std::max(1, atoi(getenv("AA_TF32_CHAIN")));
+  *out = st;
+  return AA_OK;
+}
+
+void tf_destroy(TfState* st) {
+  if (!st) return;
+  for (auto& p : st->plans) cudaFree(p.w2f);
+  delete st;
+}
+
+void tf_invalidate_weights(TfState* st) { if (st) st->weights_valid = false; }
+
+// one activation buffer = two planes of max_act_elems floats (+ alignment slack)
+int64_t tf_workspace_bytes(const std::vector<ConvLayer>& layers, int64_t batch, int64_t n) {
+  return 3 * (tc_max_act_elems(layers, batch, n) * 8 + 1024) + 1024;
+}
+
+static CUresult tf_act_map(EncodeTiledFn encode, CUtensorMap* tm, float* buf, int64_t view_c, int64_t view_rows, int64_t batch,
+                           int64_t batch_stride_elems, int64_t plane_elems) {
+  cuuint64_t dims[4] = {(cuuint64_t)view_c, (cuuint64_t)view_rows, (cuuint64_t)batch, 2};
+  cuuint64_t strides[3] = {(cuuint64_t)view_c * 4, (cuuint64_t)batch_stride_elems * 4, (cuuint64_t)plane_elems * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)BM, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, buf, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+int tf_forward(TfState* st, const std::vector<ConvLayer>& layers, const std::vector<float*>& w, const std::vector<float*>& bvec,
+               const float* const* stems_host, const float* faders_host, int n_stems, int64_t batch, int64_t n, int apply_tanh,
+               float* y, void* workspace, cudaStream_t stream) {
+  AA_REQUIRE(batch < 65536 && n < (1LL << 30), "problem too large");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!st->weights_valid) {
+    for (size_t i = 1; i < layers.size(); ++i) {
+      const auto& ly = layers[i];
+      const LayerPlan& p = st->plans[i];
+      PackArgs pa{};
+      pa.n_taps = p.n_taps; pa.cin = ly.cin; pa.k = ly.k; pa.cout = ly.cout; pa.k_total = p.k_total;
+      int kc = 0;
+      for (int j = 0; j < p.n_taps; ++j) {
+        pa.tap_col0[j] = p.tap_col0[j]; pa.tap_width[j] = p.tap_width[j]; pa.tap_kbase[j] = p.tap_kbase[j]; pa.tap_kcol[j] = kc;
+        kc += p.tap_width[j];
+      }
+      const long long tot = (long long)ly.cout * (p.k_total + tf_id_cols(ly));
+      pack_weights_tf32_kernel<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, stream>>>(w[i], p.w2f, pa, tf_id_cols(ly));
+      AA_LAUNCH_CHECK();
+    }
+    st->weights_valid = true;
+  }
+  const int64_t plane_elems = tc_max_act_elems(layers, batch, n);
+  const int64_t buf_bytes = plane_elems * 8 + 1024;
+  unsigned char* wsb = reinterpret_cast<unsigned char*>(workspace);
+  wsb += (1024 - (reinterpret_cast<uintptr_t>(wsb) & 1023)) & 1023;
+  float* buf[3] = {reinterpret_cast<float*>(wsb), reinterpret_cast<float*>(wsb + buf_bytes), reinterpret_cast<float*>(wsb + 2 * buf_bytes)};
+  int cur = 0, res_buf = -1;
+  int64_t l = n;
+  {  // ---- layer 0 on CUDA cores ----
+    const auto& ly = layers[0];
+    const int64_t lout = (l + 2 * ly.pad - (int64_t)ly.dil * (ly.k - 1) - 1) / ly.stride + 1;
+    AA_REQUIRE(lout == l && ly.dil == 1, "first layer must be a 'same' convolution");
+    L0fArgs a{};
+    a.n_in = n_stems;
+    for (int s = 0; s < n_stems; ++s) { a.x[s] = stems_host[s]; a.fader[s] = faders_host ? faders_host[s] : 1.0f; }
+    a.cin = ly.cin; a.k = ly.k; a.pad = ly.pad; a.n = (int)n; a.lpad = (int)rows_padded(lout);
+    a.w = w[0]; a.bias = bvec[0]; a.out_hi = buf[0]; a.out_lo = buf[0] + plane_elems; a.row_stride = rows_padded(lout);
+    conv_l0_tf32_kernel<<<dim3((unsigned)((a.lpad + kL0fPos - 1) / kL0fPos), (unsigned)batch), 256, 0, stream>>>(a);
+    AA_LAUNCH_CHECK();
+    l = lout;
+  }
+  for (size_t i = 1; i < layers.size(); ++i) {
+    const auto& ly = layers[i];
+    const LayerPlan& p = st->plans[i];
+    const int64_t lout = (l + 2 * ly.pad - (int64_t)ly.dil * (ly.k - 1) - 1) / ly.stride + 1;
+    AA_REQUIRE(lout >= 1, "input too short for layer %zu", i);
+    const bool last = (i + 1 == layers.size());
+    int dst = 0;
+    while (dst == cur || dst == res_buf) ++dst;
+    if (ly.role == ROLE_RES_FIRST) res_buf = cur;
+    const bool res = ly.role == ROLE_RES_SECOND;
+    AA_REQUIRE(!res || (res_buf >= 0 && lout == l), "residual layer %zu without a saved input", i);
+    const int64_t in_rows_alloc = rows_padded(l);
+    const int64_t view_rows = (l + p.view_s - 1) / p.view_s;
+    CUtensorMap tmA, tmB, tmR;
+    CUresult r = tf_act_map(encode, &tmA, buf[cur], p.view_c, view_rows, batch, in_rows_alloc * ly.cin, plane_elems);
+    AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, tf32) failed for layer %zu: %d", i, (int)r);
+    tmR = tmA;
+    if (res) {   // the ResidualUnit's input x: [B][rows_padded(l)][cout], rows >= l read as zeros
+      r = tf_act_map(encode, &tmR, buf[res_buf], ly.cout, l, batch, in_rows_alloc * ly.cout, plane_elems);
+      AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(R, tf32) failed for layer %zu: %d", i, (int)r);
+    }
+    const int bn = std::min(ly.cout, 128);
+    AA_REQUIRE(ly.cout % bn == 0 && bn % 32 == 0, "cout=%d must be a multiple of 32 (and of 128 above 128) on the 3xTF32 path", ly.cout);
+    const int kt_ext = p.k_total + tf_id_cols(ly);
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)kt_ext, (cuuint64_t)ly.cout, 2};
+      cuuint64_t strides[2] = {(cuuint64_t)kt_ext * 4, (cuuint64_t)ly.cout * kt_ext * 4};
+      cuuint32_t box[3] = {32, (cuuint32_t)bn, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.w2f, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, tf32) failed for layer %zu: %d", i, (int)r);
+    }
+    TfArgs a{};
+    a.n_chunks = 0;
+    for (int j = 0; j < p.n_taps; ++j)
+      for (int c = 0; c < p.tap_width[j]; c += 32) {
+        a.chunk_off[a.n_chunks] = (short)p.tap_off[j];
+        a.chunk_col[a.n_chunks] = (short)(p.tap_col0[j] + c);
+        ++a.n_chunks;
+      }
+    a.n_main = a.n_chunks;
+    if (res)
+      for (int c = 0; c < bn; c += 32) { a.chunk_off[a.n_chunks] = 0; a.chunk_col[a.n_chunks] = (short)c; ++a.n_chunks; }
+    AA_REQUIRE(a.n_chunks <= kTfMaxChunks, "too many K chunks (%d)", a.n_chunks);
+    a.chain = st->chain;
+    a.bn = bn; a.n_tiles_n = ly.cout / bn; a.m_tiles = (int)((rows_padded(lout) + BM - 1) / BM);
+    a.tiles = batch * a.m_tiles * a.n_tiles_n;
+    a.lout = (int)lout; a.lpad = (int)rows_padded(lout); a.cout = ly.cout;
+    a.bias = bvec[i];
+    a.out_hi = last ? nullptr : buf[dst];
+    a.out_lo = last ? nullptr : buf[dst] + plane_elems;
+    a.out_f32 = last ? y : nullptr;
+    a.out_row_stride = rows_padded(lout);
+    a.elu = ly.elu; a.tanh_out = (last && apply_tanh) ? 1 : 0;
+    AA_REQUIRE(last || ly.elu, "hidden layers without ELU are not supported on the 3xTF32 path (layer %zu)", i);
+    const int stage_bytes = 2 * BM * 128 + 2 * bn * 128;
+    const int fixed = 1024 + 256 + ly.cout * 4;            // alignment slack, barriers, bias
+    a.stages = std::max(2, std::min(8, (st->max_smem - fixed) / stage_bytes));
+    const int smem = a.stages * stage_bytes + fixed;
+    AA_REQUIRE(smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);
+    const int grid = (int)std::min<long long>(a.tiles, aa::num_sms());
+    conv_tf32_kernel<<<grid, kTfThreads, smem, stream>>>(tmA, tmB, tmR, a);
+    AA_LAUNCH_CHECK();
+    if (res) res_buf = -1;
     cur = dst;
     l = lout;
   }

@@ -40,7 +40,7 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v);
 
 __global__ void __launch_bounds__(256) conv1d_f32_kernel(const ConvArgs a) {
   __shared__ float Xs[CK][XW];
-  __shared__ float Ws[CK][8][CT + 1];   // [ci][k][co]
+  __shared__ __align__(16) float Ws[CK][8][CT + 4];   // [ci][k][co]: rows 16-byte aligned (float4 loads of 4 output channels)
   const int b = blockIdx.z;
   const int co0 = blockIdx.y * CT, l0 = blockIdx.x * LT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: positions, ty: channels
@@ -68,12 +68,11 @@ __global__ void __launch_bounds__(256) conv1d_f32_kernel(const ConvArgs a) {
 #pragma unroll 2
     for (int ci = 0; ci < CK; ++ci) {
       for (int kk = 0; kk < a.k; ++kk) {
-        float wv[4], xv[4];
+        const float4 w4 = *reinterpret_cast<const float4*>(&Ws[ci][kk][ty * 4]);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        float xv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          wv[e] = Ws[ci][kk][ty * 4 + e];
-          xv[e] = Xs[ci][(tx * 4 + e) * a.stride + kk * a.dil];
-        }
+        for (int e = 0; e < 4; ++e) xv[e] = Xs[ci][(tx * 4 + e) * a.stride + kk * a.dil];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -135,6 +134,7 @@ struct AaEncoder {
   std::vector<aa::ConvLayer> layers;
   std::vector<float*> w, b;          // device fp32 copies, [cout][cin][k] / [cout]
   aa::TcState* tc = nullptr;         // bf16 tensor-core path state (conv_tc.cu), created lazily
+  aa::TfState* tf = nullptr;         // 3xTF32 tensor-core path state (conv_tf32.cuh), created lazily
   int total_stride = 1;
 };
 
@@ -168,6 +168,7 @@ int aa_encoder_destroy(AaEncoder* e) {
   for (auto p : e->w) cudaFree(p);
   for (auto p : e->b) cudaFree(p);
   aa::tc_destroy(e->tc);
+  aa::tf_destroy(e->tf);
   delete e;
   return AA_OK;
 }
@@ -190,6 +191,7 @@ int aa_encoder_set_weights(AaEncoder* e, int layer, const float* w_dev, const fl
                           (cudaStream_t)stream));
   AA_CUDA(cudaMemcpyAsync(e->b[layer], b_dev, sizeof(float) * l.cout, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (e->tc) aa::tc_invalidate_weights(e->tc);
+  if (e->tf) aa::tf_invalidate_weights(e->tf);
   return AA_OK;
 }
 
@@ -215,6 +217,7 @@ int64_t aa_encoder_workspace_bytes(const AaEncoder* e, int64_t batch, int64_t n,
   if (!e) return 0;
   const int64_t elems = max_act_elems(e, batch, n);
   if (dtype == AA_DTYPE_BF16) return aa::tc_workspace_bytes(e->layers, batch, n);
+  if (dtype == AA_DTYPE_TF32X3) return aa::tf_workspace_bytes(e->layers, batch, n);
   return 3 * elems * (int64_t)sizeof(float) + 256;
 }
 
@@ -231,6 +234,14 @@ int aa_encoder_forward(AaEncoder* e, const float* const* stems_host, const float
       if (rc != AA_OK) return rc;
     }
     return aa::tc_forward(e->tc, e->layers, e->w, e->b, stems_host, faders_host, n_stems, batch, n, apply_tanh, y, workspace,
+                          (cudaStream_t)stream);
+  }
+  if (dtype == AA_DTYPE_TF32X3) {
+    if (!e->tf) {
+      int rc = aa::tf_create(&e->tf, e->layers);
+      if (rc != AA_OK) return rc;
+    }
+    return aa::tf_forward(e->tf, e->layers, e->w, e->b, stems_host, faders_host, n_stems, batch, n, apply_tanh, y, workspace,
                           (cudaStream_t)stream);
   }
   AA_REQUIRE(dtype == AA_DTYPE_F32, "unknown dtype %d", dtype);

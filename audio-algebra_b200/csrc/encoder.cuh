@@ -25,4 +25,14 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
                const float* const* stems_host, const float* faders_host, int n_stems, int64_t batch, int64_t n, int apply_tanh,
                float* y, void* workspace, cudaStream_t stream);
 
+// 3xTF32 tensor-core path (conv_tf32.cuh): fp32-grade results, same call shape as the bf16 path
+struct TfState;
+int tf_create(TfState** st, const std::vector<ConvLayer>& layers);
+void tf_destroy(TfState* st);
+void tf_invalidate_weights(TfState* st);
+int64_t tf_workspace_bytes(const std::vector<ConvLayer>& layers, int64_t batch, int64_t n);
+int tf_forward(TfState* st, const std::vector<ConvLayer>& layers, const std::vector<float*>& w, const std::vector<float*>& b,
+               const float* const* stems_host, const float* faders_host, int n_stems, int64_t batch, int64_t n, int apply_tanh,
+               float* y, void* workspace, cudaStream_t stream);
+
 }  // namespace aa

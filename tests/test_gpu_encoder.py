@@ -110,6 +110,28 @@ def test_bf16_mode_cosine(setup):
     assert cos.min().item() >= 0.999, cos
 
 
+def test_tf32x3_mode_is_fp32_grade(setup):
+    """3xTF32 tensor-core path (conv_tf32.cuh): fp32 operands as hi + lo TF32 parts, three MMAs per K step.  Same tolerance as
+    the fp32 path against the oracle, and agreement with the CUDA-core fp32 path far inside it."""
+    aab, O, enc_o, dv = setup
+    dvt = aab.DVAEWrapper(debug=False, compute_dtype="tf32x3")
+    dvt.model.load_oracle_weights(enc_o)
+    dvt = dvt.cuda()
+    for shape, seed in [((2, 2, 16384), 21), ((3, 2, 5000), 22), ((1, 2, 128), 23), ((1, 2, 131072), 24), ((5, 2, 3001), 25)]:
+        x = _x(shape, seed)
+        y = dvt.encode(x.cuda())
+        ref = O.dvae_encode_it(enc_o, x)
+        assert tuple(y.shape) == tuple(ref.shape)
+        assert rel_l2(y, ref) < 1e-3, (shape, rel_l2(y, ref))
+        y32 = dv.encode(x.cuda())
+        assert rel_l2(y, y32) < 2e-5, (shape, rel_l2(y, y32))
+    s0, s1 = _x((2, 2, 8192), 5), _x((2, 2, 8192), 6)
+    f = [1.4630, -0.5718]
+    y = dvt.model.encode_mix([s0.cuda(), s1.cuda()], f)
+    assert rel_l2(y, O.dvae_encode(enc_o, f[0] * s0 + f[1] * s1)) < 1e-3
+    assert tuple(dvt.encode(torch.zeros(0, 2, 4096, device="cuda")).shape) == (0, 64, 32)
+
+
 def test_bf16_fused_residual_units_match_layerwise(setup):
     """The fused ResidualUnit kernel (conv_ru.cuh: k7 -> ELU -> k1 -> +x -> ELU in one tcgen05 kernel, C = 32 / 64) against
     the layer-by-layer tcgen05 path (AA_NO_RU_FUSION=1 at handle creation): same bf16 operands, so the two agree to
