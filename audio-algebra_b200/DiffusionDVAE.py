@@ -40,7 +40,7 @@ _lib.register({
     "aa_encoder_forward": (_i, [_p, _pp, C.POINTER(_f), _i, _i64, _i64, _i, _i, _p, _p, _p]),
 })
 
-DTYPES = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "tf32x3": 2, "3xtf32": 2}
+DTYPES = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "tf32x3": 2, "3xtf32": 2, "fp32_cuda_cores": 3}
 
 
 class _Handles:
@@ -77,7 +77,8 @@ class _EncoderBlock(nn.Module):
 class SoundStreamXLEncoder(nn.Module):
     """Conv1d(in->cap,k7) ELU [ResUnit(1) ELU ResUnit(3) ELU ResUnit(9) ELU Conv1d(k=2s,stride s) ELU]* Conv1d(->latent,k3).
     The nn.Conv1d children only hold parameters (default PyTorch init, state_dict, .to()); the arithmetic is
-    one aa_encoder_forward call.  `compute_dtype`: 'fp32' (CUDA-core exact path) or 'bf16' (tcgen05)."""
+    one aa_encoder_forward call.  `compute_dtype`: 'fp32' (fp32-grade: 3xTF32 tcgen05 kernels where the layer shapes allow, else CUDA cores),
+    'tf32x3' / 'fp32_cuda_cores' (force one or the other) or 'bf16' (tcgen05, cosine >= 0.999)."""
 
     def __init__(self, in_channels=2, capacity=32, latent_dim=64, c_mults=[2, 4, 8, 16, 32], strides=[4, 4, 2, 2, 2],
                  compute_dtype="fp32"):

@@ -925,6 +925,28 @@ struct TfState {
 
 static int tf_id_cols(const ConvLayer& l) { return l.role == ROLE_RES_SECOND ? l.cout : 0; }
 
+// Quiet shape check (no error message): can this layer table run on the 3xTF32 path?  Mirrors tf_create / plan_layer / tf_forward.
+bool tf_eligible(const std::vector<ConvLayer>& layers) {
+  if (layers.size() < 2) return false;
+  const ConvLayer& l0 = layers[0];
+  if (l0.stride != 1 || l0.cout != 32 || l0.cin > 4 || l0.k > 7 || l0.dil != 1 || 2 * l0.pad != l0.k - 1 || !l0.elu) return false;
+  for (size_t i = 1; i < layers.size(); ++i) {
+    const ConvLayer& l = layers[i];
+    const bool last = i + 1 == layers.size();
+    if (l.cin % 32 != 0 || l.cout % 32 != 0 || (l.cout > 128 && l.cout % 128 != 0)) return false;
+    if (!last && !l.elu) return false;
+    if (l.stride == 1) {
+      if (l.k > 9) return false;
+    } else if (!(l.k == 2 * l.stride && l.pad == (l.stride + 1) / 2 && l.dil == 1 && l.stride % 2 == 0)) {
+      return false;
+    }
+    const int k_total = (l.stride == 1 ? l.k : 2 * l.stride) * l.cin;
+    if (k_total / 32 + (l.role == ROLE_RES_SECOND ? 4 : 0) > kTfMaxChunks) return false;
+    if (l.role == ROLE_RES_SECOND && (l.cin != l.cout || l.stride != 1 || l.k != 1)) return false;
+  }
+  return true;
+}
+
 int tf_create(TfState** out, const std::vector<ConvLayer>& layers) {
   AA_REQUIRE(get_encode_fn() != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   AA_REQUIRE(layers.size() >= 2 && layers[0].stride == 1 && layers[0].cout == 32 && layers[0].cin <= 4 && layers[0].k <= 7,
@@ -1069,7 +1091,7 @@ int tf_forward(TfState* st, const std::vector<ConvLayer>& layers, const std::vec
     a.elu = ly.elu; a.tanh_out = (last && apply_tanh) ? 1 : 0;
     AA_REQUIRE(last || ly.elu, "hidden layers without ELU are not supported on the 3xTF32 path (layer %zu)", i);
     const int stage_bytes = 2 * BM * 128 + 2 * bn * 128;
-    const int fixed = 1024 + 256 + ly.cout * 4;            // alignment slack, barriers, bias
+    const int fixed = 1024 + 512 + ly.cout * 4;            // alignment slack, barriers, bias
     a.stages = std::max(2, std::min(8, (st->max_smem - fixed) / stage_bytes));
     const int smem = a.stages * stage_bytes + fixed;
     AA_REQUIRE(smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);

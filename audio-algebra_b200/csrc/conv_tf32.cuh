@@ -8,7 +8,7 @@
 // in one chain: 4.3e-5 relative error, all of it bias; 38 such layers gave 4.4e-5 on the embeddings against 1.4e-6 for plain
 // fp32).  So the MMA warp closes a chain every `chain` K chunks (2 chunks = 24 MMAs by default), hands that TMEM slot to the
 // epilogue warps and continues in the next slot; the epilogue warps sum the partial accumulators in registers with ordinary
-// round-to-nearest fp32 adds.  Each of the two epilogue groups owns two 128-column TMEM slots, so the draining overlaps the MMAs.
+// round-to-nearest fp32 adds.  Each of the two epilogue groups owns 256 TMEM columns = 2 .. 8 accumulator slots, so the draining overlaps the MMAs.
 //
 // The residual of a ResidualUnit's 1x1 conv rides on the tensor core as well: x (hi and lo planes) times an identity block
 // appended to the weight matrix -- two extra MMAs per K step of 8 instead of per-thread global loads in the epilogue.
@@ -21,7 +21,7 @@
 #pragma once
 
 constexpr int kTfMaxChunks = 144;      // 128 conv chunks (8 x 512 channels of a strided view) + 16 residual chunks
-constexpr int kTfSlots = 4;            // TMEM accumulator slots (4 x 128 columns)
+constexpr int kTfSlots = 16;           // TMEM accumulator slots at most: 8 per epilogue group (256 columns per group / bn, capped)
 constexpr int kTfThreads = 64 + 256;   // warp 0: TMA, warp 1: MMA, 2 epilogue groups of 4 warps; 320 threads -> 200 registers each
 
 struct TfArgs {
@@ -85,13 +85,14 @@ __global__ void __launch_bounds__(kTfThreads, 1) conv_tf32_kernel(const __grid_c
   auto pfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };                // chain complete in TMEM slot i
   auto pempty_bar = [&](int i) { return bars + 8u * (2 * a.stages + kTfSlots + i); };    // slot i drained
   const uint32_t tmem_slot = bars + 8u * (2 * a.stages + 2 * kTfSlots);
-  const uint32_t sbias = bars + 256u;                                                    // cout floats
+  const uint32_t sbias = bars + 512u;                                                    // cout floats
+  const uint32_t nsl = min(8u, 256u / (uint32_t)a.bn);                                   // slots per epilogue group (power of two)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (kTfSlots * a.bn <= 128) ? 128 : (kTfSlots * a.bn <= 256 ? 256 : 512);
+  const uint32_t tmem_cols = (2u * nsl * a.bn <= 256u) ? 256u : 512u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < kTfSlots; ++i) { mbar_init(pfull_bar(i), 1); mbar_init(pempty_bar(i), 4); }
+    for (int i = 0; i < 2 * (int)nsl; ++i) { mbar_init(pfull_bar(i), 1); mbar_init(pempty_bar(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) conv_tf32_kernel(const __grid_c
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int s = 0;
       uint32_t ph = 0;
-      // Each epilogue group owns two of the four slots (2 g, 2 g + 1) and alternates between them chain by chain, so a slot's
+      // Each epilogue group owns half of the slots (nsl = 256 columns / bn of them, at most 8) and rotates through them chain by chain, so a slot's
       // barriers are only ever waited on by one group, phase after phase.  (With slots shared across the groups a group skips the
       // phases the other one handles, and a parity wait two phases ahead can pass on the stale phase.)
       uint32_t cg[2] = {0u, 0u};                            // chains issued so far for the tiles of each group
@@ -154,8 +155,8 @@ __global__ void __launch_bounds__(kTfThreads, 1) conv_tf32_kernel(const __grid_c
         const int g = it & 1;
         for (int q0 = 0; q0 < a.n_chunks; q0 += a.chain, ++cg[g]) {
           const uint32_t c = cg[g];
-          const uint32_t slot = 2u * g + (c & 1u);
-          mbar_wait(pempty_bar(slot), ((c >> 1) & 1u) ^ 1u);
+          const uint32_t slot = nsl * g + (c & (nsl - 1u));
+          mbar_wait(pempty_bar(slot), ((c / nsl) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + slot * (uint32_t)a.bn;
           const int q1 = min(q0 + a.chain, a.n_chunks);
@@ -200,8 +201,8 @@ __global__ void __launch_bounds__(kTfThreads, 1) conv_tf32_kernel(const __grid_c
       float sum[128];
       uint32_t c = (uint32_t)(it >> 1) * (uint32_t)chains_per_tile;   // this group's chain counter (same sequence as the MMA warp's)
       for (int j = 0; j < chains_per_tile; ++j, ++c) {
-        const uint32_t slot = 2u * grp + (c & 1u);
-        mbar_wait(pfull_bar(slot), (c >> 1) & 1u);
+        const uint32_t slot = nsl * grp + (c & (nsl - 1u));
+        mbar_wait(pfull_bar(slot), (c / nsl) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * (uint32_t)a.bn;
 #pragma unroll

@@ -136,6 +136,7 @@ struct AaEncoder {
   aa::TcState* tc = nullptr;         // bf16 tensor-core path state (conv_tc.cu), created lazily
   aa::TfState* tf = nullptr;         // 3xTF32 tensor-core path state (conv_tf32.cuh), created lazily
   int total_stride = 1;
+  bool tf_ok = false;                // layer table supported by the 3xTF32 path
 };
 
 extern "C" {
@@ -152,6 +153,7 @@ int aa_encoder_create(const AaEncoderCfg* cfg, AaEncoder** out) {
   e->w.assign(e->layers.size(), nullptr);
   e->b.assign(e->layers.size(), nullptr);
   for (int i = 0; i < cfg->n_blocks; ++i) e->total_stride *= cfg->strides[i];
+  e->tf_ok = aa::tf_eligible(e->layers);
   for (size_t i = 0; i < e->layers.size(); ++i) {
     const auto& l = e->layers[i];
     AA_CUDA(cudaMalloc(&e->w[i], sizeof(float) * (size_t)l.cout * l.cin * l.k));
@@ -205,6 +207,13 @@ static int64_t max_act_elems(const AaEncoder* e, int64_t batch, int64_t n) {
   return mx;
 }
 
+// AA_DTYPE_F32 asks for fp32-grade results, not for a particular pipe: layer tables the 3xTF32 kernels support run there (same
+// measured accuracy against float64 as the CUDA-core kernel, ~10x its speed); AA_DTYPE_F32_CUDA_CORES or the environment
+// variable AA_ENC_FP32_CUDA_CORES=1 selects the CUDA-core kernel.
+static bool fp32_on_tensor_cores(const AaEncoder* e) {
+  return e->tf_ok && getenv("AA_ENC_FP32_CUDA_CORES") == nullptr;
+}
+
 int aa_encoder_out_length(const AaEncoder* e, int64_t n, int64_t* t_out) {
   AA_REQUIRE(e && t_out, "NULL argument");
   int64_t l = n;
@@ -218,7 +227,9 @@ int64_t aa_encoder_workspace_bytes(const AaEncoder* e, int64_t batch, int64_t n,
   const int64_t elems = max_act_elems(e, batch, n);
   if (dtype == AA_DTYPE_BF16) return aa::tc_workspace_bytes(e->layers, batch, n);
   if (dtype == AA_DTYPE_TF32X3) return aa::tf_workspace_bytes(e->layers, batch, n);
-  return 3 * elems * (int64_t)sizeof(float) + 256;
+  const int64_t cuda_core_bytes = 3 * elems * (int64_t)sizeof(float) + 256;
+  if (dtype == AA_DTYPE_F32 && fp32_on_tensor_cores(e)) return std::max(cuda_core_bytes, aa::tf_workspace_bytes(e->layers, batch, n));
+  return cuda_core_bytes;
 }
 
 int aa_encoder_forward(AaEncoder* e, const float* const* stems_host, const float* faders_host, int n_stems, int64_t batch,
@@ -236,7 +247,7 @@ int aa_encoder_forward(AaEncoder* e, const float* const* stems_host, const float
     return aa::tc_forward(e->tc, e->layers, e->w, e->b, stems_host, faders_host, n_stems, batch, n, apply_tanh, y, workspace,
                           (cudaStream_t)stream);
   }
-  if (dtype == AA_DTYPE_TF32X3) {
+  if (dtype == AA_DTYPE_TF32X3 || (dtype == AA_DTYPE_F32 && fp32_on_tensor_cores(e))) {
     if (!e->tf) {
       int rc = aa::tf_create(&e->tf, e->layers);
       if (rc != AA_OK) return rc;
@@ -244,7 +255,7 @@ int aa_encoder_forward(AaEncoder* e, const float* const* stems_host, const float
     return aa::tf_forward(e->tf, e->layers, e->w, e->b, stems_host, faders_host, n_stems, batch, n, apply_tanh, y, workspace,
                           (cudaStream_t)stream);
   }
-  AA_REQUIRE(dtype == AA_DTYPE_F32, "unknown dtype %d", dtype);
+  AA_REQUIRE(dtype == AA_DTYPE_F32 || dtype == AA_DTYPE_F32_CUDA_CORES, "unknown dtype %d", dtype);
   AA_REQUIRE(batch <= 65535, "fp32 path: batch <= 65535 per call");
   const int64_t elems = max_act_elems(e, batch, n);
   float* buf[3] = {reinterpret_cast<float*>(workspace), reinterpret_cast<float*>(workspace) + elems,

@@ -27,6 +27,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
 
 // 3xTF32 tensor-core path (conv_tf32.cuh): fp32-grade results, same call shape as the bf16 path
 struct TfState;
+bool tf_eligible(const std::vector<ConvLayer>& layers);
 int tf_create(TfState** st, const std::vector<ConvLayer>& layers);
 void tf_destroy(TfState* st);
 void tf_invalidate_weights(TfState* st);

@@ -38,6 +38,7 @@ extern "C" {
 #define AA_DTYPE_F32 0
 #define AA_DTYPE_BF16 1
 #define AA_DTYPE_TF32X3 2 /* encoder only: fp32 operands split into two TF32 parts, three tcgen05 MMAs per K step, fp32 accumulate */
+#define AA_DTYPE_F32_CUDA_CORES 3 /* encoder only: the CUDA-core fp32 kernel, whatever the layer shapes */
 
 int aa_version(void);
 const char* aa_last_error(void);
@@ -166,9 +167,10 @@ int64_t aa_encoder_workspace_bytes(const AaEncoder* enc, int64_t batch, int64_t 
 /* y [B][latent][T'] f32 = encoder(sum_j faders_host[j] * stems[j]) (tanh applied iff apply_tanh).
  * stems_host: host array of n_stems (1..4) device pointers to [B][in_channels][n] f32 tensors; the
  * fader-scaled sum (aa_mixer.py:303,309) is fused into the first layer's load.  dtype selects the
- * arithmetic: AA_DTYPE_F32 (CUDA-core fp32, exact-parity path), AA_DTYPE_TF32X3 (tcgen05 kind::tf32 with hi/lo operand
- * split: fp32-grade results, needs capacity 32 and channel counts that are multiples of 32) or AA_DTYPE_BF16 (tcgen05
- * kind::f16, fp32 accumulate). */
+ * arithmetic: AA_DTYPE_F32 (fp32-grade results: the 3xTF32 tensor-core kernels when the layer shapes allow -- capacity 32,
+ * channel counts multiples of 32, even strides -- else the CUDA-core fp32 kernel), AA_DTYPE_TF32X3 (tcgen05 kind::tf32 with
+ * hi/lo operand split, error if the shapes do not allow), AA_DTYPE_F32_CUDA_CORES (always the CUDA-core kernel) or
+ * AA_DTYPE_BF16 (tcgen05 kind::f16, fp32 accumulate). */
 int aa_encoder_forward(AaEncoder* enc, const float* const* stems_host, const float* faders_host, int n_stems,
                        int64_t batch, int64_t n, int apply_tanh, int dtype, float* y, void* workspace, void* stream);
 

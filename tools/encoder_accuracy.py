@@ -15,7 +15,7 @@ with torch.no_grad():
     ref32 = O.dvae_encode_it(enc_o, x)
 rel = lambda a, b: ((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm()).item()
 out = {"oracle_fp32_cpu": rel(ref32, ref)}
-for mode in ("fp32", "tf32x3", "bf16"):
+for mode in ("fp32_cuda_cores", "tf32x3", "bf16"):
     dv = aab.DVAEWrapper(debug=False, compute_dtype=mode)
     dv.model.load_oracle_weights(enc_o)
     dv = dv.cuda()

@@ -7,7 +7,7 @@ import audio_algebra_b200 as aab
 N = int(os.environ.get("N", 131072))
 GF_PER_CHUNK = 68.17 * N / 131072
 res = {}
-for dtype, batches in (("bf16", [int(b) for b in os.environ.get("BS", "8,64,256").split(",")]), ("tf32x3", [int(b) for b in os.environ.get("BS_TF", "8,64").split(",")]), ("fp32", [2])):
+for dtype, batches in (("bf16", [int(b) for b in os.environ.get("BS", "8,64,256").split(",")]), ("tf32x3", [int(b) for b in os.environ.get("BS_TF", "8,64").split(",")]), ("fp32_cuda_cores", [2])):
     dv = aab.DVAEWrapper(debug=False, compute_dtype=dtype).cuda()
     for B in batches:
         x = torch.rand(B, 2, N, device="cuda") - 0.5
