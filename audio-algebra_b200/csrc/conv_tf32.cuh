@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(kTfThreads, 1) conv_tf32_kernel(const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer: both planes of the A box and of the weight box per K chunk =====================
-    if (lane == 0) {
+    // (whole warp runs the loop so that addresses and coordinates stay in uniform registers; one elected lane issues)
+    {
+      const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
       int s = 0;
       uint32_t ph = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x) {
@@ -124,24 +126,30 @@ __global__ void __launch_bounds__(kTfThreads, 1) conv_tf32_kernel(const __grid_c
         const int nt = r % a.n_tiles_n, mt = r / a.n_tiles_n;
         const int m0 = mt * BM, n0 = nt * a.bn;
         for (int q = 0; q < a.n_chunks; ++q) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), STAGE);
-          const uint32_t sa = base + (uint32_t)s * STAGE;
-          const CUtensorMap* am = (q < a.n_main) ? &tmA : &tmR;
+          const uint32_t fb = ubars + 8u * s;
+          mbar_wait(ubars + 8u * (a.stages + s), ph ^ 1u);
+          const uint32_t sa = ubase + (uint32_t)s * STAGE;
+          const bool main = q < a.n_main;
           // a residual chunk multiplies the identity block: of x's channels only [n0, n0 + bn) reach this N tile
-          const int col = (q < a.n_main) ? a.chunk_col[q] : n0 + a.chunk_col[q], row = m0 + a.chunk_off[q];
-          const int wcol = (q < a.n_main) ? q * 32 : a.n_main * 32 + n0 + a.chunk_col[q];
-          tma_load_4d(sa, am, full_bar(s), col, row, b, 0);
-          tma_load_4d(sa + A_BYTES, am, full_bar(s), col, row, b, 1);
-          tma_load_3d(sa + 2u * A_BYTES, &tmB, full_bar(s), wcol, n0, 0);
-          tma_load_3d(sa + 2u * A_BYTES + B_BYTES, &tmB, full_bar(s), wcol, n0, 1);
+          const int col = main ? a.chunk_col[q] : n0 + a.chunk_col[q], row = m0 + a.chunk_off[q];
+          const int wcol = main ? q * 32 : a.n_main * 32 + n0 + a.chunk_col[q];
+          if (elect_one()) {
+            mbar_expect_tx(fb, STAGE);
+            if (main) { tma_load_4d(sa, &tmA, fb, col, row, b, 0); tma_load_4d(sa + A_BYTES, &tmA, fb, col, row, b, 1); }
+            else      { tma_load_4d(sa, &tmR, fb, col, row, b, 0); tma_load_4d(sa + A_BYTES, &tmR, fb, col, row, b, 1); }
+            tma_load_3d(sa + 2u * A_BYTES, &tmB, fb, wcol, n0, 0);
+            tma_load_3d(sa + 2u * A_BYTES + B_BYTES, &tmB, fb, wcol, n0, 1);
+          }
           if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: 3 x 4 MMAs (K = 8 each) per chunk, a new accumulator slot every `chain` chunks =====================
-    if (lane == 0) {
+    {
+      // warp-uniform copies the compiler can keep in uniform registers (a shuffle from lane 0 is uniform by construction)
+      const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0);
+      const uint32_t utmem = __shfl_sync(0xffffffffu, tmem_base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
       // instruction descriptor: D = F32, A = B = TF32 (format 2), both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int s = 0;
@@ -149,35 +157,36 @@ __global__ void __launch_bounds__(kTfThreads, 1) conv_tf32_kernel(const __grid_c
       // Each epilogue group owns half of the slots (nsl = 256 columns / bn of them, at most 8) and rotates through them chain by chain, so a slot's
       // barriers are only ever waited on by one group, phase after phase.  (With slots shared across the groups a group skips the
       // phases the other one handles, and a parity wait two phases ahead can pass on the stale phase.)
-      uint32_t cg[2] = {0u, 0u};                            // chains issued so far for the tiles of each group
+      uint32_t cg0 = 0u, cg1 = 0u;                          // chains issued so far for the tiles of each group
       int it = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int g = it & 1;
-        for (int q0 = 0; q0 < a.n_chunks; q0 += a.chain, ++cg[g]) {
-          const uint32_t c = cg[g];
+        for (int q0 = 0; q0 < a.n_chunks; q0 += a.chain) {
+          const uint32_t c = g ? cg1 : cg0;
+          if (g) ++cg1; else ++cg0;
           const uint32_t slot = nsl * g + (c & (nsl - 1u));
-          mbar_wait(pempty_bar(slot), ((c / nsl) & 1u) ^ 1u);
+          mbar_wait((ubars + 8u * (2 * a.stages + kTfSlots + slot)), ((c / nsl) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + slot * (uint32_t)a.bn;
+          const uint32_t tmem_d = utmem + slot * (uint32_t)a.bn;
           const int q1 = min(q0 + a.chain, a.n_chunks);
           for (int q = q0; q < q1; ++q) {
-            mbar_wait(full_bar(s), ph);
+            mbar_wait((ubars + 8u * s), ph);
             tc_fence_after();
-            const uint32_t sa = base + (uint32_t)s * STAGE;
+            const uint32_t sa = ubase + (uint32_t)s * STAGE;
             const uint64_t a_hi = make_desc<64>(sa), a_lo = make_desc<64>(sa + A_BYTES);
             const uint64_t w_hi = make_desc<64>(sa + 2u * A_BYTES), w_lo = make_desc<64>(sa + 2u * A_BYTES + B_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_lo + (uint64_t)(k * 2), w_hi + (uint64_t)(k * 2), idesc, (q != q0 || k != 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) if (elect_one()) umma_tf32(tmem_d, a_lo + (uint64_t)(k * 2), w_hi + (uint64_t)(k * 2), idesc, (q != q0 || k != 0) ? 1u : 0u);
             if (q < a.n_main) {                             // (the identity block of a residual chunk has no lo part)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), w_lo + (uint64_t)(k * 2), idesc, 1u);
+              for (int k = 0; k < 4; ++k) if (elect_one()) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), w_lo + (uint64_t)(k * 2), idesc, 1u);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), w_hi + (uint64_t)(k * 2), idesc, 1u);
-            umma_commit(empty_bar(s));
+            for (int k = 0; k < 4; ++k) if (elect_one()) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), w_hi + (uint64_t)(k * 2), idesc, 1u);
+            if (elect_one()) umma_commit((ubars + 8u * (a.stages + s)));
             if (++s == a.stages) { s = 0; ph ^= 1u; }
           }
-          umma_commit(pfull_bar(slot));
+          if (elect_one()) umma_commit((ubars + 8u * (2 * a.stages + slot)));
         }
       }
     }
