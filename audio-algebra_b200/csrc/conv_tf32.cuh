@@ -57,6 +57,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same MMA with the two shared-memory descriptors given as their low words only: the high word of a SWIZZLE_128B K-major
+// descriptor (SBO = 1024 B, version 1, layout 2) is the constant 0x40004040, and the low word is (address >> 4) | LBO field, so a
+// K step of 32 bytes is "+ 2" on a 32-bit value -- half the uniform-register traffic per issued MMA of the 64-bit form.
+__device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
 __device__ __forceinline__ void stg_v8(float* p, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -173,16 +189,20 @@ __global__ void __launch_bounds__(kTfThreads, 1) conv_tf32_kernel(const __grid_c
             mbar_wait((ubars + 8u * s), ph);
             tc_fence_after();
             const uint32_t sa = ubase + (uint32_t)s * STAGE;
-            const uint64_t a_hi = make_desc<64>(sa), a_lo = make_desc<64>(sa + A_BYTES);
-            const uint64_t w_hi = make_desc<64>(sa + 2u * A_BYTES), w_lo = make_desc<64>(sa + 2u * A_BYTES + B_BYTES);
+            const uint32_t a_hi = ((sa & 0x3FFFFu) >> 4) | 0x10000u, a_lo = a_hi + (A_BYTES >> 4);
+            const uint32_t w_hi = a_hi + ((2u * A_BYTES) >> 4), w_lo = w_hi + (B_BYTES >> 4);
+            const bool lead = elect_one();
+            if (lead) {
+              // small terms first, the hi x hi term last
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (elect_one()) umma_tf32(tmem_d, a_lo + (uint64_t)(k * 2), w_hi + (uint64_t)(k * 2), idesc, (q != q0 || k != 0) ? 1u : 0u);
-            if (q < a.n_main) {                             // (the identity block of a residual chunk has no lo part)
+              for (int k = 0; k < 4; ++k) umma_tf32_lo(tmem_d, a_lo + 2u * k, w_hi + 2u * k, idesc, (q != q0 || k != 0) ? 1u : 0u);
+              if (q < a.n_main) {                             // (the identity block of a residual chunk has no lo part)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) if (elect_one()) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), w_lo + (uint64_t)(k * 2), idesc, 1u);
+                for (int k = 0; k < 4; ++k) umma_tf32_lo(tmem_d, a_hi + 2u * k, w_lo + 2u * k, idesc, 1u);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32_lo(tmem_d, a_hi + 2u * k, w_hi + 2u * k, idesc, 1u);
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (elect_one()) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), w_hi + (uint64_t)(k * 2), idesc, 1u);
             if (elect_one()) umma_commit((ubars + 8u * (a.stages + s)));
             if (++s == a.stages) { s = 0; ph ^= 1u; }
           }
