@@ -188,71 +188,59 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(xfull(s)) : "memory");
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: the whole warp runs the loop (uniform registers), one elected lane issues (elect_one) =====================
-    {
-      const uint32_t ub = __shfl_sync(0xffffffffu, base, 0), utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t usW7 = ub + Cfg::OFF_W7, usW1 = ub + Cfg::OFF_W1, usX = ub + Cfg::OFF_X, usT = ub + Cfg::OFF_T;
-      auto uxfull = [&](int s) { return ub + 8u * s; };
-      auto uxempty = [&](int s) { return ub + 8u * (NX + s); };
-      auto uacc1full = [&](int g) { return ub + 8u * (2 * NX + g); };
-      auto uacc1empty = [&](int g) { return ub + 8u * (2 * NX + NG + g); };
-      auto utfull = [&](int g) { return ub + 8u * (2 * NX + 2 * NG + g); };
-      auto uacc2full = [&](int g) { return ub + 8u * (2 * NX + 3 * NG + g); };
-      auto uacc2empty = [&](int g) { return ub + 8u * (2 * NX + 4 * NG + g); };
-      auto uwfull = [&](int s) { return ub + 8u * (2 * NX + 5 * NG + s); };
-      auto uwempty = [&](int s) { return ub + 8u * (2 * NX + 5 * NG + Cfg::NW + s); };
-      (void)uxempty; (void)uwfull; (void)uwempty; (void)usW7;
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       auto issue_k1 = [&](int j) {
         const int g = j % NG;
         const uint32_t n = (uint32_t)(j / NG);
-        mbar_wait(utfull(g), n & 1u);
-        mbar_wait(uacc2empty(g), (n & 1u) ^ 1u);
+        mbar_wait(tfull(g), n & 1u);
+        mbar_wait(acc2empty(g), (n & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = utmem + (uint32_t)(g * 2 * C + C);
-        const uint32_t ta = usT + (uint32_t)g * Cfg::TBYTES;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(g * 2 * C + C);
+        const uint32_t ta = sT + (uint32_t)g * Cfg::TBYTES;
 #pragma unroll
         for (int kk = 0; kk < C / 16; ++kk)
-          if (elect_one()) umma_bf16(tmem_d, make_desc_ns(ta + (uint32_t)(2 * kk) * Cfg::TS, Cfg::TS), make_desc_ns(usW1 + (uint32_t)(2 * kk) * Cfg::WS, Cfg::WS),
+          umma_bf16(tmem_d, make_desc_ns(ta + (uint32_t)(2 * kk) * Cfg::TS, Cfg::TS), make_desc_ns(sW1 + (uint32_t)(2 * kk) * Cfg::WS, Cfg::WS),
                     idesc, kk != 0 ? 1u : 0u);
-        if (elect_one()) umma_commit(uacc2full(g));
+        umma_commit(acc2full(g));
       };
       int it = 0;
       uint32_t wcount = 0;   // streamed weight chunks consumed so far
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int g = it % NG, s = it % NX;
         const uint32_t n = (uint32_t)(it / NG);
-        mbar_wait(uxfull(s), (uint32_t)(it / NX) & 1u);
-        mbar_wait(uacc1empty(g), (n & 1u) ^ 1u);
+        mbar_wait(xfull(s), (uint32_t)(it / NX) & 1u);
+        mbar_wait(acc1empty(g), (n & 1u) ^ 1u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core reads
         tc_fence_after();
-        const uint32_t tmem_d = utmem + (uint32_t)(g * 2 * C);
-        const uint32_t xa = usX + (uint32_t)s * Cfg::XBYTES;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(g * 2 * C);
+        const uint32_t xa = sX + (uint32_t)s * Cfg::XBYTES;
         if constexpr (Cfg::STREAM) {
           // k7 weights arrive chunk by chunk ([C][64 K] = tap j, K half h) through the ring filled by the weight producer warp
 #pragma unroll 1
           for (int q = 0; q < 7 * (C / 64); ++q, ++wcount) {
             const int j = q / (C / 64), h = q - j * (C / 64), ws = (int)(wcount % Cfg::NW);
-            mbar_wait(uwfull(ws), (wcount / Cfg::NW) & 1u);
+            mbar_wait(wfull(ws), (wcount / Cfg::NW) & 1u);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_after();
-            const uint32_t wb = usW7 + (uint32_t)ws * Cfg::WCH;
+            const uint32_t wb = sW7 + (uint32_t)ws * Cfg::WCH;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              if (elect_one()) umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(8 * h + 2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
+              umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(8 * h + 2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
                         make_desc_ns(wb + (uint32_t)(2 * kk) * Cfg::WS, Cfg::WS), idesc, (q | kk) != 0 ? 1u : 0u);
-            if (elect_one()) umma_commit(uwempty(ws));           // frees the ring stage when these MMAs retire
+            umma_commit(wempty(ws));           // frees the ring stage when these MMAs retire
           }
         } else {
 #pragma unroll 1
           for (int j = 0; j < 7; ++j) {
 #pragma unroll
             for (int kk = 0; kk < C / 16; ++kk)
-              if (elect_one()) umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
-                        make_desc_ns(usW7 + (uint32_t)(j * P + 2 * kk) * Cfg::WS, Cfg::WS), idesc, (j | kk) != 0 ? 1u : 0u);
+              umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
+                        make_desc_ns(sW7 + (uint32_t)(j * P + 2 * kk) * Cfg::WS, Cfg::WS), idesc, (j | kk) != 0 ? 1u : 0u);
           }
         }
-        if (elect_one()) umma_commit(uacc1full(g));
+        umma_commit(acc1full(g));
         if (it >= LAG) issue_k1(it - LAG);   // the oldest tile still waiting for its 1x1 conv: its operand is (nearly) ready by now
       }
       for (int j = (it >= LAG ? it - LAG : 0); j < it; ++j) issue_k1(j);

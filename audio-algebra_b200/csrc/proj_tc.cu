@@ -66,11 +66,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem] * B[smem]^T, fp32 containers read as TF32, fp32 accumulate, issued by one thread
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -154,30 +149,25 @@ __global__ void __launch_bounds__(kProjTcThreads, 1) proj_fwd_tc_kernel(const Pr
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===================== MMA issuer: the whole warp runs the loop so that addresses and descriptors stay in uniform
-    // registers; one elected lane issues (under `if (lane == 0)` every tcgen05.mma costs an ELECT / R2UR.BROADCAST / BRA.U.ANY loop)
-    {
-      const uint32_t usAhi = __shfl_sync(0xffffffffu, sAhi, 0), usAlo = __shfl_sync(0xffffffffu, sAlo, 0);
-      const uint32_t usWhi = __shfl_sync(0xffffffffu, sWhi, 0), usWlo = __shfl_sync(0xffffffffu, sWlo, 0);
-      const uint32_t utmem = __shfl_sync(0xffffffffu, tmem_base, 0), uafull = __shfl_sync(0xffffffffu, afull, 0);
-      const uint32_t uaccfull = __shfl_sync(0xffffffffu, accfull, 0);
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
       // instruction descriptor: D = F32, A = B = TF32 (format 2), both K-major, N = 64, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PD >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
       uint32_t n = 0;
       for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         for (int l = 0; l < 4; ++l, ++n) {
-          mbar_wait(uafull, n & 1u);
+          mbar_wait(afull, n & 1u);
           tc_fence_after();
-          const uint32_t whi = usWhi + (uint32_t)l * W_BYTES, wlo = usWlo + (uint32_t)l * W_BYTES;
+          const uint32_t whi = sWhi + (uint32_t)l * W_BYTES, wlo = sWlo + (uint32_t)l * W_BYTES;
 #pragma unroll
           for (int term = 0; term < 3; ++term) {   // a_lo w_hi, a_hi w_lo, a_hi w_hi
-            const uint32_t ab = (term == 0) ? usAlo : usAhi, wb = (term == 1) ? wlo : whi;
+            const uint32_t ab = (term == 0) ? sAlo : sAhi, wb = (term == 1) ? wlo : whi;
 #pragma unroll
             for (int kk = 0; kk < PD / 8; ++kk)
-              if (elect_one()) umma_tf32(utmem, make_desc_ns(ab + (uint32_t)(2 * kk) * PSA, PSA), make_desc_ns(wb + (uint32_t)(2 * kk) * PSW, PSW), idesc,
-                                         (term | kk) != 0 ? 1u : 0u);
+              umma_tf32(tmem_base, make_desc_ns(ab + (uint32_t)(2 * kk) * PSA, PSA), make_desc_ns(wb + (uint32_t)(2 * kk) * PSW, PSW), idesc,
+                        (term | kk) != 0 ? 1u : 0u);
           }
-          if (elect_one()) umma_commit(uaccfull);
+          umma_commit(accfull);
         }
       }
     }
