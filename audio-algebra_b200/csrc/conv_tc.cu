@@ -187,10 +187,9 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
   if (warp >= 2 + 4 * a.n_epi) {
     // unused epilogue warps of this launch configuration
   } else if (warp == 0) {
-    // ===================== TMA producer =====================
-    // (lane-0 loops here and in the MMA warp: with N = 256 tiles these loops are not issue bound, and the warp-wide / elected
-    //  form that the 3xTF32 kernel needs measured 3 % slower on this kernel)
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues: see elect_one) =====================
+    {
+      const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
       int s = 0;
       uint32_t ph = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x) {
@@ -199,18 +198,23 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
         const int nt = r % a.n_tiles_n, mt = r / a.n_tiles_n;
         const int m0 = mt * BM, n0 = nt * a.bn;
         for (int q = 0; q < a.n_chunks; ++q) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
-          const uint32_t sa = base + (uint32_t)s * STAGE;
-          tma_load_3d(sa, &tmA, full_bar(s), a.chunk_col[q], m0 + a.chunk_off[q], b);
-          tma_load_2d(sa + A_BYTES, &tmB, full_bar(s), q * BK, n0);
+          const uint32_t fb = ubars + 8u * s;
+          mbar_wait(ubars + 8u * (a.stages + s), ph ^ 1u);
+          const uint32_t sa = ubase + (uint32_t)s * STAGE;
+          if (elect_one()) {
+            mbar_expect_tx(fb, A_BYTES + B_BYTES);
+            tma_load_3d(sa, &tmA, fb, a.chunk_col[q], m0 + a.chunk_off[q], b);
+            tma_load_2d(sa + A_BYTES, &tmB, fb, q * BK, n0);
+          }
           if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues: see elect_one) =====================
+    {
+      const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
+      const uint32_t utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int s = 0;
@@ -218,21 +222,21 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
       int it = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int acc = it % a.n_acc;
-        mbar_wait(tempty_bar(acc), (((uint32_t)(it / a.n_acc)) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        mbar_wait(ubars + 8u * (2 * a.stages + kMaxAcc + acc), (((uint32_t)(it / a.n_acc)) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.bn);
+        const uint32_t tmem_d = utmem + (uint32_t)(acc * a.bn);
         for (int q = 0; q < a.n_chunks; ++q) {
-          mbar_wait(full_bar(s), ph);
+          mbar_wait(ubars + 8u * s, ph);
           tc_fence_after();
-          const uint32_t sa = base + (uint32_t)s * STAGE;
+          const uint32_t sa = ubase + (uint32_t)s * STAGE;
           const uint64_t da = make_desc<BK>(sa), db = make_desc<BK>(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)   // 16 bf16 = 32 bytes along K inside the swizzle atom
-            umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (q | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(s));           // frees the smem stage when these MMAs retire
+            if (elect_one()) umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (q | k) != 0 ? 1u : 0u);
+          if (elect_one()) umma_commit(ubars + 8u * (a.stages + s));   // frees the smem stage when these MMAs retire
           if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));           // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(ubars + 8u * (2 * a.stages + acc));   // accumulator complete -> epilogue
       }
     }
   } else {
