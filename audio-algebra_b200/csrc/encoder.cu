@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -222,13 +223,25 @@ int aa_encoder_out_length(const AaEncoder* e, int64_t n, int64_t* t_out) {
   return AA_OK;
 }
 
+// The tensor-core paths walk a large batch in sub-batches through the WHOLE layer stack (not layer by layer over the full batch), so
+// that the activation workspace stops growing with the batch: 2^25 samples per channel per sub-batch for bf16 (256 chunks of 2^17:
+// 8 GB of workspace instead of 160 GB at B = 4096), 2^23 for the fp32 planes.  Speed is unchanged (B = 512: 49.0 ms either way;
+// sub-batches of 64 chunks and less lose 1-5 %, `tools/time_subbatch.py`) -- the 9 % that B = 64 gains over B = 512 in
+// profiles/encode_sweep_r01.json is burst clocks, not L2 residency.  AA_ENC_SUB_SAMPLES overrides the target.
+static int64_t sub_batch(int64_t batch, int64_t n, bool bf16) {
+  static const int64_t forced = getenv("AA_ENC_SUB_SAMPLES") ? std::max<int64_t>(1, atoll(getenv("AA_ENC_SUB_SAMPLES"))) : 0;
+  const int64_t target = forced ? forced : (bf16 ? (256LL << 17) : (64LL << 17));
+  return std::min(batch, std::max<int64_t>(1, target / std::max<int64_t>(n, 1)));
+}
+
 int64_t aa_encoder_workspace_bytes(const AaEncoder* e, int64_t batch, int64_t n, int dtype) {
   if (!e) return 0;
   const int64_t elems = max_act_elems(e, batch, n);
-  if (dtype == AA_DTYPE_BF16) return aa::tc_workspace_bytes(e->layers, batch, n);
-  if (dtype == AA_DTYPE_TF32X3) return aa::tf_workspace_bytes(e->layers, batch, n);
+  const int64_t sb = sub_batch(batch, n, dtype == AA_DTYPE_BF16);
+  if (dtype == AA_DTYPE_BF16) return aa::tc_workspace_bytes(e->layers, sb, n);
+  if (dtype == AA_DTYPE_TF32X3) return aa::tf_workspace_bytes(e->layers, sb, n);
   const int64_t cuda_core_bytes = 3 * elems * (int64_t)sizeof(float) + 256;
-  if (dtype == AA_DTYPE_F32 && fp32_on_tensor_cores(e)) return std::max(cuda_core_bytes, aa::tf_workspace_bytes(e->layers, batch, n));
+  if (dtype == AA_DTYPE_F32 && fp32_on_tensor_cores(e)) return std::max(cuda_core_bytes, aa::tf_workspace_bytes(e->layers, sb, n));
   return cuda_core_bytes;
 }
 
@@ -239,21 +252,32 @@ int aa_encoder_forward(AaEncoder* e, const float* const* stems_host, const float
   AA_REQUIRE(batch >= 0 && n >= 1, "bad shape");
   if (batch == 0) return AA_OK;
   for (int s = 0; s < n_stems; ++s) AA_REQUIRE(stems_host[s] != nullptr, "stem %d is NULL", s);
-  if (dtype == AA_DTYPE_BF16) {
-    if (!e->tc) {
+  const bool bf16 = dtype == AA_DTYPE_BF16;
+  if (bf16 || dtype == AA_DTYPE_TF32X3 || (dtype == AA_DTYPE_F32 && fp32_on_tensor_cores(e))) {
+    if (bf16 && !e->tc) {
       int rc = aa::tc_create(&e->tc, e->layers);
       if (rc != AA_OK) return rc;
     }
-    return aa::tc_forward(e->tc, e->layers, e->w, e->b, stems_host, faders_host, n_stems, batch, n, apply_tanh, y, workspace,
-                          (cudaStream_t)stream);
-  }
-  if (dtype == AA_DTYPE_TF32X3 || (dtype == AA_DTYPE_F32 && fp32_on_tensor_cores(e))) {
-    if (!e->tf) {
+    if (!bf16 && !e->tf) {
       int rc = aa::tf_create(&e->tf, e->layers);
       if (rc != AA_OK) return rc;
     }
-    return aa::tf_forward(e->tf, e->layers, e->w, e->b, stems_host, faders_host, n_stems, batch, n, apply_tanh, y, workspace,
-                          (cudaStream_t)stream);
+    int64_t t_out = 0;
+    int rc = aa_encoder_out_length(e, n, &t_out);
+    if (rc != AA_OK) return rc;
+    const int64_t sb = sub_batch(batch, n, bf16);
+    for (int64_t b0 = 0; b0 < batch; b0 += sb) {
+      const int64_t nb = std::min(sb, batch - b0);
+      const float* stems_sub[4];
+      for (int s = 0; s < n_stems; ++s) stems_sub[s] = stems_host[s] + b0 * e->cfg.in_channels * n;
+      float* y_sub = y + b0 * e->cfg.latent_dim * t_out;
+      rc = bf16 ? aa::tc_forward(e->tc, e->layers, e->w, e->b, stems_sub, faders_host, n_stems, nb, n, apply_tanh, y_sub, workspace,
+                                 (cudaStream_t)stream)
+                : aa::tf_forward(e->tf, e->layers, e->w, e->b, stems_sub, faders_host, n_stems, nb, n, apply_tanh, y_sub, workspace,
+                                 (cudaStream_t)stream);
+      if (rc != AA_OK) return rc;
+    }
+    return AA_OK;
   }
   AA_REQUIRE(dtype == AA_DTYPE_F32 || dtype == AA_DTYPE_F32_CUDA_CORES, "unknown dtype %d", dtype);
   AA_REQUIRE(batch <= 65535, "fp32 path: batch <= 65535 per call");

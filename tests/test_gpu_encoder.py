@@ -221,3 +221,28 @@ def test_encode_all_bulk_loop_matches_batch_by_batch(setup):
     refm = mel.encode(data.cuda()).cpu()
     assert torch.equal(aab.encode_all(mel, data, batch_size=3), refm)
     assert rel_l2(ref[:4], O.dvae_encode_it(enc_o, data[:4])) < 1e-3
+
+
+def test_sub_batched_walk_matches_single_pass(setup, tmp_path):
+    """Large batches are walked in sub-batches through the whole layer stack (encoder.cu sub_batch); forced small here through
+    AA_ENC_SUB_SAMPLES in a subprocess, ragged last sub-batch included: bit-identical embeddings, both tensor-core modes."""
+    import os, subprocess, sys
+    code = r"""
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+import audio_algebra_b200 as aab
+torch.manual_seed(0)
+for mode in ("bf16", "fp32"):
+    dv = aab.DVAEWrapper(debug=False, compute_dtype=mode).cuda()
+    x = torch.rand(7, 2, 4096, device="cuda") - 0.5
+    torch.save(dv.encode(x).cpu(), os.environ["OUT"] + mode)
+"""
+    outs = {}
+    for tag, sub in (("one", str(1 << 30)), ("sub", str(3 * 4096))):
+        env = dict(os.environ, AA_ENC_SUB_SAMPLES=sub, OUT=str(tmp_path / f"{tag}_"))
+        subprocess.run([sys.executable, "-c", code], env=env, check=True, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        outs[tag] = {m: torch.load(str(tmp_path / f"{tag}_{m}")) for m in ("bf16", "fp32")}
+    for m in ("bf16", "fp32"):
+        assert tuple(outs["one"][m].shape) == (7, 64, 32)
+        assert torch.equal(outs["one"][m], outs["sub"][m]), m
