@@ -31,6 +31,8 @@ _SIGS = {
     "aa_stft_out_shape": (_i, [_p, _i64, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "aa_stft_complex_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
     "aa_stft_power_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
+    "aa_stft_complex_tf_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
+    "aa_stft_power_tf_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
     "aa_stft_mel_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
     "aa_magdphase_f32": (_i, [_p, _i64, _i64, _i64, _p, _p]),
     "aa_stft_mel_f32_host": (_i, [_p, _p, _i64, _i64, _i, _p, _i64]),

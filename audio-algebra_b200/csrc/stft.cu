@@ -55,6 +55,7 @@ struct StftArgs {
   const int* mel_off4;    // [n_mels] offset (in float4) into mel_w4
   const float4* mel_w4;   // padded filter weights, pre-multiplied by 0.25 (P holds 4|X|^2)
   float* out;
+  int out_tf;           // complex / power output layout: 0 = [row][freq][frame], 1 = [row][frame][freq] (torch.stft's own memory layout)
   int wav_aligned16;
   long long n_tiles;      // fast path: row pairs x tiles_per_pair
   const int4* mel_steps;  // fast path: [kWarps][mel_steps_per_warp + 1][4] step headers, then the step weights
@@ -372,6 +373,19 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
         // q=0: bins [0,256)  q=1: [256,512)  q=2: [512,768] (idx 0..256)  q=3: (768,1024] (idx 1..256)
         const int lo = (q == 3) ? 1 : 0;
         const int hi = (q >= 2) ? 257 : 256;
+        if (a.out_tf) {
+          // frequency-minor output: warp = frame of the tile, lanes run along the bins -> 256-byte runs per store
+          const int fr = f0 + warp;
+          if (fr < a.n_frames) {
+            for (int r = 0; r < 2; ++r) {
+              if (rowA + r >= a.rows) break;
+              float2* obase = reinterpret_cast<float2*>(a.out) + ((rowA + r) * (long long)a.n_frames + fr) * a.n_freq + q * 256;
+              const float2* cl = CS + (warp * 2 + r) * kCStride;
+              for (int kb = lo + lane; kb < hi; kb += 32) obase[kb] = cl[kb];
+            }
+          }
+          continue;
+        }
         const int fsub = tid % kWarps, ksub = tid / kWarps;   // 32 bins x 6 frames per pass
         const int fr = f0 + fsub;
         if (fr < a.n_frames) {
@@ -497,6 +511,22 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
           }
           h = hn;
         }
+      } else if (a.out_tf) {
+        // MODE_POWER, frequency-minor output: warp = frame of the tile, lanes run along the bins.  The lane -> bin map is shifted so
+        // that every warp store starts on a 32-byte sector boundary (rows are 1025 floats long: the row start moves by 4 bytes
+        // per row), i.e. each instruction writes whole sectors except at the two ends of the row.
+        const int fr = f0 + warp;
+        if (fr < a.n_frames) {
+          const float2* pl = P + warp * kPLine;
+          for (int r = 0; r < 2; ++r) {
+            if (rowA + r >= a.rows) break;
+            const long long e0 = ((rowA + r) * (long long)a.n_frames + fr) * a.n_freq;   // element offset of bin 0
+            float* o = a.out + e0;
+            const int shift = (int)((8 - (e0 & 7)) & 7);                                  // bins before the first sector boundary
+            for (int k = lane + shift - 32; k < 1025; k += 32)
+              if (k >= 0) o[k] = 0.25f * (r == 0 ? pl[k].x : pl[k].y);
+          }
+        }
       } else {  // MODE_POWER: lanes = (32 bins) x (6 frames) -> 24-byte runs along the frame axis
         const int fsub = tid % kWarps, ksub = tid / kWarps;
         const int fr = f0 + fsub;
@@ -554,7 +584,11 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(const StftArgs a, int
   // split: k in [0, M/2]; emits bins k and M-k (and DC/Nyquist for k = 0)
   const long long orow = row * (long long)a.n_freq;
   auto emit = [&](int k, float xr, float xi) {
-    if (MODE == MODE_COMPLEX) {
+    if (MODE != MODE_MEL && a.out_tf) {
+      const long long e = (row * a.n_frames + frame) * (long long)a.n_freq + k;
+      if (MODE == MODE_COMPLEX) reinterpret_cast<float2*>(a.out)[e] = make_float2(xr, xi);
+      else a.out[e] = xr * xr + xi * xi;
+    } else if (MODE == MODE_COMPLEX) {
       reinterpret_cast<float2*>(a.out)[(orow + k) * a.n_frames + frame] = make_float2(xr, xi);
     } else if (MODE == MODE_POWER) {
       a.out[(orow + k) * a.n_frames + frame] = xr * xr + xi * xi;
@@ -800,6 +834,26 @@ __global__ void __launch_bounds__(256, 2) stft_warp_kernel(const StftArgs a, con
           const float2 v = SMEL[f * mstride + m];
           o[(long long)m * a.n_frames] = v.x;
           if (hasB) o[((long long)a.n_mels + m) * a.n_frames] = v.y;
+        }
+      } else if (a.out_tf) {
+        // frequency-minor output: warp = frame of the block, lanes run along the bins
+        const int fw = threadIdx.x >> 5, ln = threadIdx.x & 31;
+        if (f0 + fw < a.n_frames) {
+          for (int r = 0; r < (hasB ? 2 : 1); ++r) {
+            const long long e0 = ((rowA + r) * (long long)a.n_frames + f0 + fw) * n_freq;
+            if constexpr (MODE == MODE_POWER) {
+              float* o = a.out + e0;
+              const int shift = (int)((8 - (e0 & 7)) & 7);
+              for (int k = ln + shift - 32; k <= M; k += 32)
+                if (k >= 0) { const float2 v = SA[fw * ROWLEN + wk_idx<R>(k)]; o[k] = r == 0 ? v.x : v.y; }
+            } else {
+              float2* o = reinterpret_cast<float2*>(a.out) + e0;
+              for (int k = ln; k <= M; k += 32) {
+                const float2 vr = SA[fw * ROWLEN + wk_idx<R>(k)], vi = SB[fw * ROWLEN + wk_idx<R>(k)];
+                o[k] = r == 0 ? make_float2(vr.x, vi.x) : make_float2(vr.y, vi.y);
+              }
+            }
+          }
         }
       } else if constexpr (MODE == MODE_POWER) {
         float* o = a.out + (rowA * n_freq) * a.n_frames + f0 + f;
@@ -1099,7 +1153,7 @@ int aa_stft_out_shape(const AaStftPlan* p, int64_t n_in, int zero_pad, int64_t* 
 }
 
 static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
-                       float* out, cudaStream_t st) {
+                       float* out, cudaStream_t st, int out_tf = 0) {
   AA_REQUIRE(p != nullptr, "plan is NULL");
   AA_REQUIRE(rows >= 0, "rows=%lld", (long long)rows);
   if (rows == 0) return AA_OK;
@@ -1116,7 +1170,7 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
   a.window2 = p->d_window2; a.tw1 = p->d_tw1; a.tw2 = p->d_tw2;
   a.mel_start4 = p->d_mel_meta; a.mel_cnt4 = p->d_mel_meta ? p->d_mel_meta + p->n_mels : nullptr;
   a.mel_off4 = p->d_mel_meta ? p->d_mel_meta + 2 * p->n_mels : nullptr;
-  a.mel_w4 = p->d_mel_w4; a.out = out;
+  a.mel_w4 = p->d_mel_w4; a.out = out; a.out_tf = out_tf;
   a.wav_aligned16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0) ? 1 : 0;
   const bool big_out = rows * (int64_t)std::max(p->n_freq, p->n_mels) * n_frames >= (1LL << 31);
   if (p->fast && !big_out) {
@@ -1185,6 +1239,14 @@ int aa_stft_complex_f32(const AaStftPlan* plan, const float* wav, int64_t rows, 
 int aa_stft_power_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
                       float* out, void* stream) {
   return stft_launch(plan, MODE_POWER, wav, rows, n_in, zero_pad, out, (cudaStream_t)stream);
+}
+int aa_stft_complex_tf_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                           float* out, void* stream) {
+  return stft_launch(plan, MODE_COMPLEX, wav, rows, n_in, zero_pad, out, (cudaStream_t)stream, 1);
+}
+int aa_stft_power_tf_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                         float* out, void* stream) {
+  return stft_launch(plan, MODE_POWER, wav, rows, n_in, zero_pad, out, (cudaStream_t)stream, 1);
 }
 int aa_stft_mel_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
                     float* out, void* stream) {

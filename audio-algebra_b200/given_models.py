@@ -209,8 +209,11 @@ class _StftFrontEnd(GivenModelClass):
                                                           self.fb)
         return self._plans[device_index]
 
-    def _run(self, waveform, mode, out=None):
-        """waveform [..., N] float32 -> [..., F|n_mels, T].  CUDA input: stream-ordered kernel on the
+    def _run(self, waveform, mode, out=None, freq_major=False):
+        """waveform [..., N] float32 -> [..., F|n_mels, T].  Complex and power spectrograms come back as the transposed view of a
+        [..., T, F] buffer -- exactly what torch.stft / torchaudio.transforms.Spectrogram return (same shape, values AND strides
+        as the reference's tensors), and the layout the kernels write at full sector width; freq_major=True asks for a
+        contiguous [..., F, T] tensor instead.  CUDA input: stream-ordered kernel on the
         current stream.  CPU input: H2D, kernel, D2H (result returned on the CPU, like the reference
         keeps the input's device) -- the mel variant pipelines the copies in chunks; `out` may be a
         preallocated (ideally pinned) CPU tensor, as in the reference's bulk-encode loop
@@ -236,7 +239,12 @@ class _StftFrontEnd(GivenModelClass):
                 check(lib.aa_stft_mel_f32_host(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), 64))
                 return out
             x = waveform.to(f"cuda:{dev}", non_blocking=True).contiguous()
-            if mode == "complex":
+            if mode in ("complex", "power") and not freq_major:
+                out = torch.empty((*lead, n_frames, bins), dtype=torch.complex64 if mode == "complex" else torch.float32, device=x.device)
+                fn = lib.aa_stft_complex_tf_f32 if mode == "complex" else lib.aa_stft_power_tf_f32
+                check(fn(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), stream_ptr()))
+                out = out.transpose(-1, -2)
+            elif mode == "complex":
                 out = torch.empty((*lead, bins, n_frames), dtype=torch.complex64, device=x.device)
                 check(lib.aa_stft_complex_f32(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), stream_ptr()))
             elif mode == "power":
@@ -285,7 +293,7 @@ class MagDPhaseSpectrogramAE(_StftFrontEnd):
             raise ValueError("MagDPhaseSpectrogramAE.encode expects unbatched [channels, samples] input "
                              "(the reference indexes dtheta[:,:,0] and concatenates on dim 0)")
         on_cpu = not waveform.is_cuda
-        spec = self._run(waveform.cuda() if on_cpu else waveform, "complex")
+        spec = self._run(waveform.cuda() if on_cpu else waveform, "complex", freq_major=True)   # aa_magdphase_f32 reads [c][F][T]
         c, f, t = spec.shape
         out = torch.empty((2 * c, f, t), dtype=torch.float32, device=spec.device)
         with torch.cuda.device(spec.device):

@@ -74,6 +74,15 @@ int aa_stft_complex_f32(const AaStftPlan* plan, const float* wav, int64_t rows, 
 /* -> out [rows][n_fft/2+1][n_frames] f32 = |X|^2 */
 int aa_stft_power_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
                       float* out, void* stream);
+/* The same two, written frequency-minor: out [rows][n_frames][n_fft/2+1].  This is the memory layout of the reference's own
+ * tensors -- torch.stft / torchaudio Spectrogram return [.., freq, time] as a transposed VIEW of a [.., time, freq] buffer
+ * (given_models.py:161,182 call them unchanged) -- and the one the kernels write at full sector width (rows of n_fft/2+1
+ * contiguous values instead of 24..32-byte runs along a 257-frame axis).  The Python wrappers call these and return
+ * out.transpose(-1, -2): same shape, values and strides as the reference. */
+int aa_stft_complex_tf_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                           float* out, void* stream);
+int aa_stft_power_tf_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                         float* out, void* stream);
 /* -> out [rows][n_mels][n_frames] f32 */
 int aa_stft_mel_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
                     float* out, void* stream);

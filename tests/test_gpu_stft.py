@@ -223,3 +223,25 @@ def test_warp_kernel_small_n_fft(aab, n_fft, hop, shape):
     ref = O.stft_complex(x, n_fft, hop, center=False, zero_pad=False)
     out = m.encode(xc)
     assert tuple(out.shape) == tuple(ref.shape) and rel_l2(out, ref) < TOL
+
+
+@pytest.mark.parametrize("n_fft,hop,shape", [(2048, 512, (3, 2, 16384)), (1024, 256, (2, 3, 5000)), (256, 64, (1, 1, 4096)),
+                                             (4096, 1024, (2, 2, 16384)), (2048, 500, (1, 3, 9000))])
+def test_output_layouts_agree_and_match_the_reference_strides(aab, n_fft, hop, shape):
+    """Complex / power spectrograms are written frequency-minor (aa_stft_*_tf_f32) and returned as transposed views: the strides
+    torch.stft / torchaudio give the reference's tensors.  The contiguous [.., F, T] variant (freq_major=True, used by the
+    MagDPhase epilogue) must hold the same values: tile kernel, warp kernel and generic kernel, odd row counts included."""
+    import torchaudio
+    g = torch.Generator().manual_seed(n_fft + hop)
+    x = (torch.rand(*shape, generator=g) - 0.5).cuda()
+    for cls, mode, power in ((aab.SpectrogramAE, "complex", None), (aab.MagSpectrogramAE, "power", 2)):
+        m = cls(n_fft=n_fft, hop_length=hop)
+        y = m.encode(x)
+        yc = m._run(x, mode, freq_major=True)
+        assert yc.is_contiguous() and tuple(y.shape) == tuple(yc.shape)
+        assert torch.equal(y, yc)
+        m.zero_pad = False
+        ref = torchaudio.transforms.Spectrogram(n_fft=n_fft, hop_length=hop, power=power)(x.cpu())
+        y2 = m.encode(x)
+        assert tuple(y2.shape) == tuple(ref.shape) and y2.stride()[-2:] == ref.stride()[-2:] == (1, n_fft // 2 + 1)
+        assert rel_l2(torch.view_as_real(y2) if power is None else y2, torch.view_as_real(ref) if power is None else ref) < 1e-4
