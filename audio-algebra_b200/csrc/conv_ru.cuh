@@ -104,7 +104,7 @@ __device__ __forceinline__ void group_sync(int g) {
 }
 
 template <int C>
-__global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused_kernel(const RuArgs a) {
+__global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused_kernel(const __grid_constant__ CUtensorMap tmX, const RuArgs a) {
   using Cfg = RuCfg<C>;
   constexpr int P = Cfg::P, NX = Cfg::NX, NG = Cfg::NG, LAG = Cfg::LAG, kRuThreads = Cfg::THREADS;
   extern __shared__ unsigned char smem_raw[];
@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NX; ++s) { mbar_init(xfull(s), 32); mbar_init(xempty(s), 4); }
+    for (int s = 0; s < NX; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 4); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     for (int g = 0; g < NG; ++g) {
       mbar_init(acc1full(g), 1); mbar_init(acc1empty(g), 4); mbar_init(tfull(g), 4);
       mbar_init(acc2full(g), 1); mbar_init(acc2empty(g), 4);
@@ -165,27 +166,27 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
 
   const int d = a.dil;
   const int R = BM + 6 * d;   // rows of an x tile
+  const uint32_t xs = (uint32_t)R * 16u;   // panel stride of an x tile in shared memory = what one TMA box lays down: [C/8 panels][R rows][16 B]
 
   if (warp == 0) {
     // ===================== producer: x tiles (rows m0 - 3d .. m0 + 127 + 3d) =====================
-    const int pn = lane % P, r_lane = lane / P;
-    constexpr int RSTEP = 32 / P;
-    int it = 0;
-    for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
-      const int s = it % NX;
-      if (it >= NX) mbar_wait(xempty(s), (uint32_t)((it / NX) - 1) & 1u);
-      const int b = (int)(t / a.m_tiles);
-      const int m0 = (int)(t - (long long)b * a.m_tiles) * BM;
-      const __nv_bfloat16* xb = a.x + (size_t)b * (size_t)a.rows_alloc * C + pn * 8;
-      const uint32_t dst0 = sX + (uint32_t)s * Cfg::XBYTES + (uint32_t)pn * Cfg::XS;
-      for (int row = r_lane; row < R; row += RSTEP) {
-        const int grow = m0 - 3 * d + row;
-        const bool ok = grow >= 0 && grow < a.lout;
-        cp_async16(dst0 + (uint32_t)row * 16u, ok ? (const void*)(xb + (size_t)grow * C) : (const void*)a.x, ok ? 16u : 0u);
+    // ONE TMA box per tile: the tensor map views x [B][rows][C] as (8 channels = 16 B, row, panel, batch) with the panel as the
+    // outer box dimension, so the box lands directly in the no-swizzle panel layout [C/8][R][16 B]; rows outside [0, lout) are
+    // zero-filled = the conv padding.  (The first version copied 16-byte pieces with cp.async: ncu showed 3 of every 4 LDGSTS
+    // serialised into 32 shared-memory wavefronts -- 22 M of the kernel's 52 M wavefronts, the LSU data pipe at 61 %.)
+    if (lane == 0) {
+      int it = 0;
+      for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
+        const int s = it % NX;
+        if (it >= NX) mbar_wait(xempty(s), (uint32_t)((it / NX) - 1) & 1u);
+        const int b = (int)(t / a.m_tiles);
+        const int m0 = (int)(t - (long long)b * a.m_tiles) * BM;
+        mbar_expect_tx(xfull(s), xs * (uint32_t)P);
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                         sX + (uint32_t)s * Cfg::XBYTES),
+                     "l"(&tmX), "r"(xfull(s)), "r"(0), "r"(m0 - 3 * d), "r"(0), "r"(b)
+                     : "memory");
       }
-      // every lane's arrival fires when its copies have landed (count 32, no producer-side wait): the producer
-      // runs up to NX tiles ahead of the epilogue
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(xfull(s)) : "memory");
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
         const uint32_t n = (uint32_t)(it / NG);
         mbar_wait(xfull(s), (uint32_t)(it / NX) & 1u);
         mbar_wait(acc1empty(g), (n & 1u) ^ 1u);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core reads
+        // (the x tile was written by TMA, i.e. by the async proxy the tensor core reads through: no proxy fence needed here)
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(g * 2 * C);
         const uint32_t xa = sX + (uint32_t)s * Cfg::XBYTES;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
             const uint32_t wb = sW7 + (uint32_t)ws * Cfg::WCH;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(8 * h + 2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
+              umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(8 * h + 2 * kk) * xs + (uint32_t)(j * d) * 16u, xs),
                         make_desc_ns(wb + (uint32_t)(2 * kk) * Cfg::WS, Cfg::WS), idesc, (q | kk) != 0 ? 1u : 0u);
             umma_commit(wempty(ws));           // frees the ring stage when these MMAs retire
           }
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
           for (int j = 0; j < 7; ++j) {
 #pragma unroll
             for (int kk = 0; kk < C / 16; ++kk)
-              umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(2 * kk) * Cfg::XS + (uint32_t)(j * d) * 16u, Cfg::XS),
+              umma_bf16(tmem_d, make_desc_ns(xa + (uint32_t)(2 * kk) * xs + (uint32_t)(j * d) * 16u, xs),
                         make_desc_ns(sW7 + (uint32_t)(j * P + 2 * kk) * Cfg::WS, Cfg::WS), idesc, (j | kk) != 0 ? 1u : 0u);
           }
         }
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(RuCfg<C>::THREADS, (C == 32) ? 2 : 1) ru_fused
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
                        : "r"(sbias + 4u * (uint32_t)(C + c0 + 8 * q + 4)));
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr.x), "=r"(xr.y), "=r"(xr.z), "=r"(xr.w)
-                       : "r"(xres + (uint32_t)(c0 / 8 + q) * Cfg::XS));
+                       : "r"(xres + (uint32_t)(c0 / 8 + q) * xs));
           float2 y0 = __fadd2_rn(make_float2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])), make_float2(ba.x, ba.y));
           float2 y1 = __fadd2_rn(make_float2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])), make_float2(ba.z, ba.w));
           float2 y2 = __fadd2_rn(make_float2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), make_float2(bb.x, bb.y));

@@ -841,15 +841,25 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
       ra.lout = (int)lout; ra.lpad = (int)rows_padded(lout); ra.dil = ly.dil;
       ra.m_tiles = (int)((rows_padded(lout) + BM - 1) / BM);
       ra.rows_alloc = rows_padded(l); ra.tiles = batch * ra.m_tiles;
+      CUtensorMap tmX;
+      {   // x [B][rows_alloc][C] bf16 as (8 channels, row, panel, batch): box = (8, 128 + 6d rows, C/8 panels, 1)
+        cuuint64_t dims[4] = {8, (cuuint64_t)lout, (cuuint64_t)(ly.cin / 8), (cuuint64_t)batch};
+        cuuint64_t strides[3] = {(cuuint64_t)ly.cin * 2, 16, (cuuint64_t)rows_padded(l) * ly.cin * 2};
+        cuuint32_t box[4] = {8, (cuuint32_t)(BM + 6 * ly.dil), (cuuint32_t)(ly.cin / 8), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, buf[cur], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(x tile, fused unit) failed for layer %zu: %d", i, (int)r);
+      }
       if (ly.cin == 32) {
         const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms() * st->ru_ctas_per_sm[0]);
-        ru_fused_kernel<32><<<grid, RuCfg<32>::THREADS, RuCfg<32>::SMEM, stream>>>(ra);
+        ru_fused_kernel<32><<<grid, RuCfg<32>::THREADS, RuCfg<32>::SMEM, stream>>>(tmX, ra);
       } else if (ly.cin == 64) {
         const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms() * st->ru_ctas_per_sm[1]);
-        ru_fused_kernel<64><<<grid, RuCfg<64>::THREADS, RuCfg<64>::SMEM, stream>>>(ra);
+        ru_fused_kernel<64><<<grid, RuCfg<64>::THREADS, RuCfg<64>::SMEM, stream>>>(tmX, ra);
       } else {
         const int grid = (int)std::min<long long>(ra.tiles, (long long)aa::num_sms());
-        ru_fused_kernel<128><<<grid, RuCfg<128>::THREADS, RuCfg<128>::SMEM, stream>>>(ra);
+        ru_fused_kernel<128><<<grid, RuCfg<128>::THREADS, RuCfg<128>::SMEM, stream>>>(tmX, ra);
       }
       AA_LAUNCH_CHECK();
       cur = dst;
