@@ -246,3 +246,22 @@ for mode in ("bf16", "fp32"):
     for m in ("bf16", "fp32"):
         assert tuple(outs["one"][m].shape) == (7, 64, 32)
         assert torch.equal(outs["one"][m], outs["sub"][m]), m
+
+
+def test_full_size_batch_modes_agree(setup):
+    """BASELINE-size chunks (2^17 samples), a batch that the fp32 mode walks in two sub-batches (64 + ragged 16): the fp32-grade and
+    bf16 tensor-core modes agree to cosine >= 0.999 per embedding on every chunk, and the first and last chunks match the oracle."""
+    aab, O, enc_o, dv = setup
+    dvb = aab.DVAEWrapper(debug=False, compute_dtype="bf16")
+    dvb.model.load_oracle_weights(enc_o)
+    dvb = dvb.cuda()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand(80, 2, 131072, generator=g, device="cuda") - 0.5
+    y32 = dv.encode(x)
+    yb = dvb.encode(x)
+    assert tuple(y32.shape) == (80, 64, 1024)
+    cos = torch.nn.functional.cosine_similarity(y32.flatten(1).double(), yb.flatten(1).double(), dim=1)
+    assert cos.min().item() >= 0.999, cos.min().item()
+    for i in (0, 79):
+        ref = O.dvae_encode_it(enc_o, x[i:i + 1].cpu())
+        assert rel_l2(y32[i:i + 1], ref) < 1e-3, i
