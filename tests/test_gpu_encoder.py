@@ -265,3 +265,25 @@ def test_full_size_batch_modes_agree(setup):
     for i in (0, 79):
         ref = O.dvae_encode_it(enc_o, x[i:i + 1].cpu())
         assert rel_l2(y32[i:i + 1], ref) < 1e-3, i
+
+
+@pytest.mark.parametrize("in_ch,c_mults,strides,latent", [(1, [2, 4], [4, 2], 32), (2, [1, 2, 4], [2, 2, 4], 96), (4, [2], [2], 64)])
+def test_other_encoder_configs_on_the_tensor_core_paths(setup, in_ch, c_mults, strides, latent):
+    "mono / 4-channel (PQMF-style) inputs, other depths, strides and latent widths: fp32-grade and bf16 modes against the oracle"
+    aab, O, _, _ = setup
+    from audio_algebra_b200.DiffusionDVAE import SoundStreamXLEncoder
+    torch.manual_seed(11)
+    ref = O.SoundStreamXLEncoderOracle(in_channels=in_ch, capacity=32, latent_dim=latent, c_mults=c_mults, strides=strides).eval()
+    x = _x((3, in_ch, 6000), 41)
+    with torch.no_grad():
+        yr = ref(x)
+    for mode in ("tf32x3", "bf16"):
+        enc = SoundStreamXLEncoder(in_channels=in_ch, capacity=32, latent_dim=latent, c_mults=c_mults, strides=strides, compute_dtype=mode)
+        enc.load_oracle_weights(ref)
+        y = enc.cuda()(x.cuda())
+        assert tuple(y.shape) == tuple(yr.shape)
+        if mode == "tf32x3":
+            assert rel_l2(y, yr) < 1e-3, (mode, rel_l2(y, yr))
+        else:
+            cos = torch.nn.functional.cosine_similarity(y.flatten(1).double().cpu(), yr.flatten(1).double(), dim=1)
+            assert cos.min().item() >= 0.999, (mode, cos)
