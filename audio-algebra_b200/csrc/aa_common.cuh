@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include "../../include/aa_b200.h"
 
 namespace aa {
@@ -41,15 +42,40 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
     ::aa::count_launch();                                                                  \
   } while (0)
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+inline int num_sms() {   // SM count of the CURRENT device (cached per device: one process may drive several GPUs)
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: opt in once per (kernel, device).
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, int bytes) {
+  struct Slot { const void* k; int bytes[64]; };
+  static Slot slots[96] = {};
+  static int n_slots = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  const void* key = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> g(mu);
+  Slot* sl = nullptr;
+  for (int i = 0; i < n_slots; ++i)
+    if (slots[i].k == key) { sl = &slots[i]; break; }
+  if (sl && sl->bytes[dev] >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  if (!sl && n_slots < 96) { sl = &slots[n_slots++]; sl->k = key; }
+  if (sl) sl->bytes[dev] = bytes;
+  return e;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

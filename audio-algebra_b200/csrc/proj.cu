@@ -348,11 +348,7 @@ int aa_projector_half_fwd_f32(const float* const* w_host, const float* const* b_
       (reinterpret_cast<uintptr_t>(w_host[1]) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_host[2]) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(w_host[3]) & 15) == 0)
     return aa::proj_fwd_tc(w_host, b_host, x, batch, t, out, (cudaStream_t)stream);
-  static bool attr = false;
-  if (!attr) {
-    AA_CUDA(cudaFuncSetAttribute(proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
-    attr = true;
-  }
+  AA_CUDA(aa::ensure_dyn_smem(proj_fwd_kernel, kFwdSmem));   // per (kernel, device)
   const int grid = (int)std::min<long long>(a.n_tiles, 2LL * aa::num_sms());
   proj_fwd_kernel<<<grid, PTHREADS, kFwdSmem, (cudaStream_t)stream>>>(a);
   AA_LAUNCH_CHECK();
@@ -370,11 +366,7 @@ int aa_projector_half_bwd_f32(const float* const* w_host, const float* const* b_
   if (rc != AA_OK) return rc;
   AA_REQUIRE(gout && workspace && gw_host && gb_host, "NULL argument");
   if (ba.f.n_tiles == 0) return AA_OK;
-  static bool attr = false;
-  if (!attr) {
-    AA_CUDA(cudaFuncSetAttribute(proj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-    attr = true;
-  }
+  AA_CUDA(aa::ensure_dyn_smem(proj_bwd_kernel, kBwdSmem));   // per (kernel, device)
   ba.gout = gout; ba.gx = gx; ba.partials = workspace; ba.accumulate_gx = accumulate_gx;
   const int grid = (int)std::min<long long>(ba.f.n_tiles, (long long)aa::num_sms());
   proj_bwd_kernel<<<grid, PTHREADS, kBwdSmem, (cudaStream_t)stream>>>(ba);

@@ -235,11 +235,7 @@ namespace aa {
 
 // Forward of one projector half on the tensor core; requires dims = hidden = 64 with residuals.  Returns AA_OK or an error code.
 int proj_fwd_tc(const float* const* w, const float* const* b, const float* x, int64_t batch, int64_t t, float* out, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
-    AA_CUDA(cudaFuncSetAttribute(proj_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjTcSmem));
-    attr = true;
-  }
+  AA_CUDA(aa::ensure_dyn_smem(proj_fwd_tc_kernel, kProjTcSmem));   // per (kernel, device)
   ProjTcArgs a;
   for (int l = 0; l < 4; ++l) { a.w[l] = w[l]; a.b[l] = b[l]; }
   a.x = x; a.out = out; a.batch = batch; a.t = (int)t;

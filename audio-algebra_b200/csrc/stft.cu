@@ -546,6 +546,8 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
   }
 }
 
+#include "stft2048_v2.cuh"
+
 // ------------------------------------------------------------------------------------------
 // Generic kernel: one CTA per (row, frame); M = n_fft/2 complex points in shared memory.
 // ------------------------------------------------------------------------------------------
@@ -914,12 +916,123 @@ struct AaStftPlan {
   int fast_smem = 0, fast_grid_per_sm = 2;
   float2* d_wk = nullptr;        // warp kernel (n_fft <= 1024): [R][32] W_M^(lane k1), then [M] W_2M^k
   int wk_r = 0;
+  // stft2048_v2_kernel (decoupled warps; banded mel): per KW in {6, 12}
+  bool v2_mel_ok = false;        // the filterbank is a <= 2-adjacent-tap band with non-decreasing filter index
+  int4* d_v2_groups = nullptr;   // warp start indices + 48-byte group records of the banded mel walk
+  int v2_groups_len = 0;
   // resources of aa_stft_mel_f32_host (created lazily)
   cudaStream_t hstream[2] = {nullptr, nullptr};
   float* hbuf_in[2] = {nullptr, nullptr};
   float* hbuf_out[2] = {nullptr, nullptr};
   long long hbuf_rows = 0, hbuf_nin = 0, hbuf_out_per_row = 0;
 };
+
+// Banded form of the mel filterbank for stft2048_v2_kernel: every bin k feeds at most the two ADJACENT filters m_lo(k) and
+// m_lo(k) + 1 with m_lo non-decreasing in k (true for torchaudio's triangular HTK / Slaney banks; verified here on the actual
+// matrix, so a custom bank that is not of this form simply keeps the v1 kernel).  The runs of equal m_lo become "steps"
+// {first bin, bins, filter to store}: out[m] = sum_{run m} w_lo P + sum_{run m-1} w_hi P.  Steps are dealt to the KW warps as
+// contiguous ranges of about equal cost; a warp first re-walks the run before its range to get that run's w_hi sum.
+static int v2_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int n_mels) {
+  p->v2_mel_ok = false;
+  if (F != 1025 || n_mels < 1) return AA_OK;
+  std::vector<int> mlo(F);
+  std::vector<float2> w(1028, make_float2(0.f, 0.f));
+  int prev = -1;
+  for (int k = 0; k < F; ++k) {
+    int nz[3], nn = 0;
+    for (int m = 0; m < n_mels && nn < 3; ++m)
+      if (fb[(size_t)k * n_mels + m] != 0.0f) nz[nn++] = m;
+    int m;
+    if (nn > 2) return AA_OK;
+    if (nn == 2) {
+      if (nz[1] != nz[0] + 1) return AA_OK;
+      m = nz[0];
+    } else if (nn == 1) {
+      m = (prev == nz[0] - 1) ? prev : nz[0];
+    } else {
+      m = prev;
+    }
+    if (m < prev) return AA_OK;
+    mlo[k] = m;
+    prev = m;
+    w[k].x = (m >= 0) ? 0.25f * fb[(size_t)k * n_mels + m] : 0.f;
+    w[k].y = (m + 1 < n_mels) ? 0.25f * fb[(size_t)k * n_mels + m + 1] : 0.f;
+  }
+  // runs: s = m + 1 for m = -1 .. n_mels - 1 (possibly empty); groups of <= 4 bins per run
+  const int ns = n_mels + 1;
+  std::vector<int> k0(ns, 0), len(ns, 0), ng(ns, 1);
+  for (int k = 0; k < F; ++k) {
+    const int s_ = mlo[k] + 1;
+    if (len[s_] == 0) k0[s_] = k;
+    len[s_]++;
+  }
+  for (int s_ = 0; s_ < ns; ++s_) ng[s_] = std::max(1, (len[s_] + 3) / 4);
+  // contiguous partition of the runs over the 12 warps, minimising the largest cost (2 per group, 1 per run end, plus the groups of
+  // the run BEFORE the range, which the warp re-walks for its w_hi sum): binary search on the bound + greedy fill
+  auto overlap = [&](int a0) { return (a0 > 0 && len[a0 - 1] > 0) ? 2 * ng[a0 - 1] : 0; };
+  auto parts_needed = [&](long long bound, std::vector<int>* firsts) {
+    int parts = 0, s_ = 0;
+    if (firsts) firsts->clear();
+    while (s_ < ns) {
+      long long c = overlap(s_);
+      if (firsts) firsts->push_back(s_);
+      int taken = 0;
+      while (s_ < ns && (taken == 0 || c + 2 * ng[s_] + 1 <= bound)) { c += 2 * ng[s_] + 1; ++s_; ++taken; }
+      ++parts;
+    }
+    return parts;
+  };
+  long long lo_b = 1, hi_b = 0;
+  for (int s_ = 0; s_ < ns; ++s_) hi_b += 2 * ng[s_] + 1;
+  hi_b += 64;
+  while (lo_b < hi_b) {
+    const long long mid = (lo_b + hi_b) / 2;
+    if (parts_needed(mid, nullptr) <= kV2W) hi_b = mid; else lo_b = mid + 1;
+  }
+  std::vector<int> firsts;
+  parts_needed(lo_b, &firsts);
+  while ((int)firsts.size() < kV2W) firsts.push_back(ns);   // idle warps get an empty range
+  firsts.push_back(ns);
+  std::vector<int4> tab(4, make_int4(0, 0, 0, 0));
+  auto f2i = [](float v) { int i; std::memcpy(&i, &v, 4); return i; };
+  auto push_run = [&](int s_, int m_store, bool last_of_warp) {
+    const int n = ng[s_];
+    for (int gi = 0; gi < n; ++gi) {
+      const int kb = k0[s_] + 4 * gi;
+      float wv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < 4; ++j)
+        if (4 * gi + j < len[s_]) { wv[2 * j] = w[kb + j].x; wv[2 * j + 1] = w[kb + j].y; }
+      const bool last_g = gi == n - 1;
+      tab.push_back(make_int4(len[s_] > 0 ? kb * 8 : 0, (last_g ? 1 : 0) | ((last_g && last_of_warp) ? 2 : 0), m_store, 0));
+      tab.push_back(make_int4(f2i(wv[0]), f2i(wv[1]), f2i(wv[2]), f2i(wv[3])));
+      tab.push_back(make_int4(f2i(wv[4]), f2i(wv[5]), f2i(wv[6]), f2i(wv[7])));
+    }
+  };
+  auto push_dummy = [&](int flags) {
+    tab.push_back(make_int4(0, flags, -1, 0));
+    tab.push_back(make_int4(0, 0, 0, 0));
+    tab.push_back(make_int4(0, 0, 0, 0));
+  };
+  for (int wq = 0; wq < kV2W; ++wq) {
+    reinterpret_cast<int*>(tab.data())[wq] = (int)tab.size();
+    const int a0 = firsts[wq], a1 = firsts[wq + 1];
+    if (a0 >= a1) { push_dummy(3); continue; }
+    if (a0 > 0 && len[a0 - 1] > 0) push_run(a0 - 1, -1, false);               // the run before the range: only its w_hi sum is used
+    for (int s_ = a0; s_ < a1; ++s_) push_run(s_, s_ - 1, s_ == a1 - 1);      // s_ = 0 (bins below the first filter) stores nothing
+  }
+  push_dummy(3);
+  push_dummy(3);   // the walk prefetches two records past the end of a list
+  p->v2_groups_len = (int)tab.size();
+  AA_CUDA(cudaMalloc(&p->d_v2_groups, sizeof(int4) * tab.size()));
+  AA_CUDA(cudaMemcpy(p->d_v2_groups, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice));
+  p->v2_mel_ok = true;
+  return AA_OK;
+}
+
+static int v2_smem_bytes(int nbuf, int hop, int groups_len) {
+  const int span = (kV2W - 1) * hop + 2048;
+  return nbuf * span * 8 + kV2W * kV2Xb + kV2Tables + groups_len * 16 + 4 * 8 + 16;
+}
 
 extern "C" {
 #pragma GCC visibility push(default)
@@ -964,8 +1077,8 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
     }
     AA_CUDA(cudaMalloc(&p->d_lane_consts, sizeof(float) * lc.size()));
     AA_CUDA(cudaMemcpy(p->d_lane_consts, lc.data(), sizeof(float) * lc.size(), cudaMemcpyHostToDevice));
-    tw1.resize(32 * 32);
-    for (int k1 = 0; k1 < 32; ++k1)
+    tw1.resize(33 * 32);   // row 32 = W_1024^(32 lane) = W_32^lane (stft2048_v2_kernel derives rows 17..31 from rows 15..1 with it)
+    for (int k1 = 0; k1 < 33; ++k1)
       for (int n2 = 0; n2 < 32; ++n2) {
         const double th = -2.0 * PI * (double)(k1 * n2) / 1024.0;
         tw1[k1 * 32 + n2] = make_float2((float)std::cos(th), (float)std::sin(th));
@@ -1101,6 +1214,8 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
       AA_CUDA(cudaMemcpy(p->d_mel_steps, tab.data(), p->mel_hdr_bytes, cudaMemcpyHostToDevice));
       AA_CUDA(cudaMemcpy(reinterpret_cast<unsigned char*>(p->d_mel_steps) + p->mel_hdr_bytes, sw.data(), p->mel_w_bytes,
                          cudaMemcpyHostToDevice));
+      rc = v2_build_mel(p, fb, F, n_mels);
+      if (rc != AA_OK) return rc;
     }
   }
   if (p->fast) {
@@ -1125,6 +1240,7 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
 int aa_stft_plan_destroy(AaStftPlan* p) {
   if (!p) return AA_OK;
   cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4); cudaFree(p->d_mel_steps); cudaFree(p->d_lane_consts); cudaFree(p->d_wk);
+  cudaFree(p->d_v2_groups);
   for (int i = 0; i < 2; ++i) {
     if (p->hbuf_in[i]) cudaFree(p->hbuf_in[i]);
     if (p->hbuf_out[i]) cudaFree(p->hbuf_out[i]);
@@ -1173,6 +1289,42 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
   a.mel_w4 = p->d_mel_w4; a.out = out; a.out_tf = out_tf;
   a.wav_aligned16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0) ? 1 : 0;
   const bool big_out = rows * (int64_t)std::max(p->n_freq, p->n_mels) * n_frames >= (1LL << 31);
+  static const int v2_mode = getenv("AA_STFT_V2") ? atoi(getenv("AA_STFT_V2")) : 1;       // 0: v1 kernel only
+  static const int v2_nbuf = getenv("AA_STFT_NBUF") ? atoi(getenv("AA_STFT_NBUF")) : 1;     // sample ring depth wanted (1 or 2)
+  // mel: the v2 kernel's banded walk is correct but still slower end to end than the v1 tile kernel (393 vs 375 us on the headline
+  // workload: every warp walks right after the P-line rendezvous, so the walk's latency is not hidden) -- opt in with AA_STFT_V2_MEL=1
+  static const bool v2_mel = getenv("AA_STFT_V2_MEL") != nullptr && atoi(getenv("AA_STFT_V2_MEL")) != 0;
+  if (p->fast && !big_out && v2_mode && rows < (1LL << 30) && n_pad < (1LL << 30) &&
+      ((mode == MODE_MEL && p->v2_mel_ok && v2_mel) || (mode != MODE_MEL && out_tf))) {
+    const int groups_len = mode == MODE_MEL ? p->v2_groups_len : 1;
+    int dev = 0, max_smem = 0;
+    AA_CUDA(cudaGetDevice(&dev));
+    AA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int nbuf = (v2_nbuf >= 2 && v2_smem_bytes(2, p->hop, groups_len) <= max_smem) ? 2 : 1;
+    const int smem = v2_smem_bytes(nbuf, p->hop, groups_len);
+    AA_REQUIRE(smem <= max_smem, "hop=%d needs %d bytes of shared memory (limit %d)", p->hop, smem, max_smem);
+    Stft2Args b;
+    b.wav = wav; b.out = out; b.rows = (int)rows; b.n_in = (int)n_in; b.n_pad = (int)n_pad; b.n_frames = (int)n_frames;
+    b.hop = p->hop; b.center_off = a.center_off; b.tiles_per_pair = (int)((n_frames + kV2W - 1) / kV2W);
+    const int64_t nt = ((rows + 1) / 2) * b.tiles_per_pair;
+    AA_REQUIRE(nt < (1LL << 31), "problem too large for the fast STFT path");
+    b.n_tiles = (int)nt; b.n_freq = p->n_freq; b.n_mels = p->n_mels; b.wav_aligned16 = a.wav_aligned16; b.nbuf = nbuf;
+    static const int v2_diag = getenv("AA_STFT_DIAG") ? atoi(getenv("AA_STFT_DIAG")) : 0;
+    b.diag = v2_diag;
+    b.tw1 = p->d_tw1; b.lane_consts = p->d_lane_consts;
+    b.mel_groups = mode == MODE_MEL ? p->d_v2_groups : reinterpret_cast<const int4*>(p->d_tw1);
+    b.mel_groups_len = groups_len;
+    const unsigned grid = (unsigned)std::min<int64_t>(nt, (int64_t)aa::num_sms());
+#define AA_V2(MD)                                                               \
+  do {                                                                          \
+    AA_CUDA(aa::ensure_dyn_smem(stft2048_v2_kernel<MD>, smem));                 \
+    stft2048_v2_kernel<MD><<<grid, kV2W * 32, smem, st>>>(b);                   \
+  } while (0)
+    if (mode == MODE_COMPLEX) AA_V2(MODE_COMPLEX); else if (mode == MODE_POWER) AA_V2(MODE_POWER); else AA_V2(MODE_MEL);
+#undef AA_V2
+    AA_LAUNCH_CHECK();
+    return AA_OK;
+  }
   if (p->fast && !big_out) {
     a.tiles_per_pair = (int)((n_frames + kWarps - 1) / kWarps);
     const int64_t pairs = (rows + 1) / 2;

@@ -11,7 +11,7 @@ from ._lib import lib, check, ptr, stream_ptr
 from .parallel import allreduce_mean_
 from .aa_mixer import (AudioAlgebra, do_mixing, get_stems_faders, mseloss, vicreg_var_loss, vicreg_cov_loss)  # noqa: F401
 
-__all__ = ['FlatAdam', 'onecycle_lr', 'onecycle_beta1', 'mixer_losses', 'MixerTrainer']
+__all__ = ['FlatAdam', 'onecycle_lr', 'onecycle_beta1', 'mixer_losses', 'MixerTrainer', 'save_aa_checkpoint', 'load_aa_checkpoint']
 
 
 def _cos(a, b, pct):
@@ -47,6 +47,19 @@ class FlatAdam:
 
     def current_lr(self):
         return self.lr if self.total_steps is None else onecycle_lr(self.t, self.total_steps, self.max_lr)
+
+    def state_dict(self):
+        "moments, step counter (= OneCycle position) and hyper-parameters: enough to resume training bit-exactly"
+        return {'m': self.m.detach().clone(), 'v': self.v.detach().clone(), 't': int(self.t), 'lr': self.lr, 'max_lr': self.max_lr,
+                'total_steps': self.total_steps, 'betas': tuple(self.betas), 'eps': self.eps}
+
+    def load_state_dict(self, sd):
+        assert sd['m'].numel() == self.m.numel() and sd['v'].numel() == self.v.numel(), "optimizer state does not match the parameters"
+        self.m.copy_(sd['m'].to(self.m.device).reshape_as(self.m))
+        self.v.copy_(sd['v'].to(self.v.device).reshape_as(self.v))
+        self.t = int(sd['t'])
+        self.lr, self.max_lr, self.total_steps = sd['lr'], sd['max_lr'], sd['total_steps']
+        self.betas, self.eps = tuple(sd['betas']), sd['eps']
 
     def step(self, flat_grads):
         lr = self.current_lr()
@@ -85,6 +98,8 @@ class MixerTrainer:
             p.grad = self.flat_grad[off:off + n].view_as(p)
             off += n
         self.opt = FlatAdam(self.flat, lr=lr, max_lr=max_lr, total_steps=total_steps)
+        self.keep_local_grad = False   # tests / bench: keep this rank's gradient as it was BEFORE the all-reduce
+        self.local_grad = None
 
     def step(self, stems, faders, batch=None):
         """stems: list of [B,2,N] device tensors (stems[0] doubles as `batch` of the reference loop);
@@ -97,6 +112,51 @@ class MixerTrainer:
         z, yrecon = self.aa_model(y)
         losses = mixer_losses(zsum, zmix, y, yrecon, archive['ymix'], archive['ymix_recon'])
         losses['loss'].backward()
+        if self.keep_local_grad:
+            self.local_grad = self.flat_grad.clone()
         allreduce_mean_(self.flat_grad, self.group)
         self.opt.step(self.flat_grad)
         return {k: v.detach() for k, v in losses.items()}
+
+    def state_dict(self):
+        return {'aa_model': self.aa_model.state_dict(), 'opt': self.opt.state_dict()}
+
+    def load_state_dict(self, sd):
+        "parameters are copied INTO the flat buffer (the views installed by __init__ stay valid)"
+        with torch.no_grad():
+            own = self.aa_model.state_dict()
+            for k, v in sd['aa_model'].items():
+                own[k].copy_(v.to(own[k].device))
+        self.opt.load_state_dict(sd['opt'])
+
+
+def save_aa_checkpoint(aa_model, path, trainer=None, **extra):
+    """The `save_aa_checkpoint` the reference calls but never defines in the script (train_aa_mixer_accel.py:550; the notebook
+    version is a torch.save of the module).  Writes a plain dict: 'state_dict' under the reference's key names
+    (encoder.{0..3}.lin.{weight,bias}, decoder....) so that it loads into the reference's AudioAlgebra with load_state_dict,
+    plus -- when a trainer is given -- the flat Adam moments, step counter and OneCycle position for exact resume."""
+    ckpt = {'state_dict': {k: v.detach().cpu().clone() for k, v in aa_model.state_dict().items()},
+            'dims': getattr(aa_model, 'dims', None), 'hidden_dims': getattr(aa_model, 'hidden_dims', None)}
+    if trainer is not None:
+        ckpt['opt'] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in trainer.opt.state_dict().items()}
+    ckpt.update(extra)
+    torch.save(ckpt, path)
+    return path
+
+
+def load_aa_checkpoint(aa_model, path, trainer=None, map_location='cpu'):
+    "inverse of save_aa_checkpoint; also accepts a bare state_dict or a pickled module (the notebook's torch.save(model))"
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    if isinstance(ckpt, torch.nn.Module):
+        ckpt = {'state_dict': ckpt.state_dict()}
+    sd = ckpt.get('state_dict', ckpt)
+    if trainer is not None:
+        trainer.load_state_dict({'aa_model': sd, 'opt': ckpt['opt']} if 'opt' in ckpt else {'aa_model': sd, 'opt': trainer.opt.state_dict()})
+    else:
+        with torch.no_grad():
+            own = aa_model.state_dict()
+            missing = set(own) - set(sd)
+            assert not missing, f"checkpoint lacks {sorted(missing)}"
+            for k in own:
+                own[k].copy_(sd[k].to(own[k].device))
+    return ckpt

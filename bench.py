@@ -12,7 +12,10 @@ the rank's batch.
   e2e        same metric through the public API with HOST (pinned) buffers: H2D + kernel + D2H per step
   roofline   the mel kernel against the MEASURED HBM copy bandwidth (algorithmic bytes / kernel time)
   cpu_baseline  the oracle's library-call restatement of the reference (torch.stft + filterbank matmul)
-             on this box's host cores, on a bounded sample of the same workload
+             on this box's host cores, on the same 256-chunk workload
+  dp         (every N, top-level copies: encoder_audio_s_per_s, train_step_ms, allreduce_us, pca_ms, dp_parity_ok)
+             BASELINE configs[3]/[4]: per-rank bf16 encoder, MixerTrainer.step with the NCCL gradient all-reduce, the
+             all-reduce alone, sharded PCA accumulation; cross-rank parity is asserted (mismatch => rc != 0)
 `--impl reference` times that CPU path as its own arm (rank 0 only).
 """
 import argparse
@@ -45,6 +48,13 @@ def synth(batch, seed, device):
     x = 0.5 * torch.sin(6.283185307179586 * f * t + ph)
     x += 0.1 * torch.randn(batch, 2, CHUNK, generator=g, device=device)
     return x.clamp_(-1, 1)
+
+
+def numa_node_count():
+    try:
+        return len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -80,7 +90,9 @@ class ClockSampler:
                 self.Q = self.Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
-            time.sleep(0.3)
+            t0 = time.time()   # nvidia-smi needs 0.3 .. 3 s to print its first line (longer with 8 GPUs behind it): wait for it,
+            while time.time() - t0 < 8.0 and os.path.getsize(self.f.name) == 0:   # so that the timed region is really sampled
+                time.sleep(0.05)
         except Exception:
             self.p = None
 
@@ -142,7 +154,6 @@ def run_extras(dev):
     against the measured bf16 tensor peak, one data-parallel mixer training step."""
     import torch
     import audio_algebra_b200 as aab
-    from audio_algebra_b200.training import MixerTrainer
     hbm, _ = measured_peaks()
     burst, sustained, src = measured_bf16_peaks()
     out = {}
@@ -180,7 +191,7 @@ def run_extras(dev):
     del x
     # ---- conv encoder, bf16 tcgen05 path (config 5 encode sweep point): 68.17 GFLOP per 2^17-sample chunk ----
     dvb = aab.DVAEWrapper(debug=False, compute_dtype="bf16").cuda()
-    for B in (64, 256, 1024):          # points of the config-5 encode sweep
+    for B in (64, 1024):               # more points of the config-5 encode sweep (B = 256 per rank is in the `dp` section)
         xe = synth(B, 99, dev)
         ms = timed(lambda: dvb.encode(xe), 5 if B <= 256 else 3)
         tf = B * 68.17 / ms            # GFLOP / ms = TFLOP/s
@@ -211,18 +222,8 @@ def run_extras(dev):
                                     "h2d_bytes": data_h.numel() * 4, "d2h_bytes": reps_h.numel() * 4,
                                     "note": "encode_all(DVAEWrapper bf16, pinned host dataset [512,2,131072]) wall clock incl. H2D and D2H (three streams)"}
     del data_h, reps_h
-    # ---- one mixer training step (config 3: 2 stems, batch 512 x 2^16 samples, bf16 encoder, fp32 projector / losses / Adam) ----
-    Bm, Nm = 512, 65536
-    torch.manual_seed(2)
-    aa = aab.AudioAlgebra(64, 64).cuda()
-    trainer = MixerTrainer(dvb.model, aa, total_steps=100)
+    Nm = 65536
     g = torch.Generator(device=dev).manual_seed(7)
-    stems = [torch.rand(Bm, 2, Nm, generator=g, device=dev) - 0.5 for _ in range(2)]
-    ms = timed(lambda: trainer.step(stems, [1.4630, -0.5718]), 3, warm=1)
-    out["mixer_train_step"] = {"ms": ms, "batch": Bm, "chunk_samples": Nm, "stems": 2, "encoder_passes": 4,
-                               "audio_s_per_s": Bm * Nm / SR / (ms * 1e-3),
-                               "note": "train_aa_mixer_accel step: do_mixing (3 encodes) + batch encode, projector fwd/bwd, 4 loss terms, flat Adam"}
-    del stems, trainer
     # ---- config 4: effects step (4 encodes as one 4B batch + projector + guesses + losses, fwd + bwd) and PCA accumulation ----
     Be = 256
     batch = {k: torch.rand(Be, 2, Nm, generator=g, device=dev) - 0.5 for k in ("a1", "b1", "a2", "b2")}
@@ -237,22 +238,169 @@ def run_extras(dev):
     ms = timed(effects_step, 3, warm=1)
     out["effects_step"] = {"ms": ms, "batch": Be, "chunk_samples": Nm, "audio_s_per_s": 4 * Be * Nm / SR / (ms * 1e-3),
                            "note": "train_aa_effects step: a1,b1,a2,b2 encoded as one 4B batch, projector enc/dec, effect guesses, 4 loss terms, backward"}
-    from audio_algebra_b200.pca import RunningCovariance
-    ys = torch.tanh(torch.randn(Be, 64, Nm // 128, generator=g, device=dev))
-    rc = RunningCovariance(64, dev)
-    ms = timed(lambda: rc.update(ys), 10)
-    out["pca_accumulate"] = {"ms": ms, "latents": list(ys.shape), "GBps": ys.numel() * 4 / ms / 1e6, "hbm_frac": ys.numel() * 4 / ms / 1e6 / hbm,
-                             "note": "calc_effects_pca loop body: 64x64 scatter straight from [B,64,T'] latents (reads them once)"}
     return out
+
+
+def run_dp(dev, world, rank, steps=3):
+    """BASELINE.json configs[3]/[4] under the driver's clock, at EVERY world size (weak scaling, per-rank shards):
+    the bf16 encoder on 256 x 2^17 chunks per rank, MixerTrainer.step on 512 x 2^16 per rank with the real gradient all-reduce
+    (train_aa_mixer_accel.py:495-545), the all-reduce alone (133 120 B, the only collective of the step) and the PCA
+    accumulation + its 4 097-float all-reduce (calc_effects_pca.py:76-94).  Cross-rank parity is ASSERTED, not reported:
+    after two steps the replicated parameters must be bit-identical on all ranks, the all-reduced gradient must equal the
+    mean of the per-rank gradients, the reduced PCA numerator must be bit-identical; a mismatch raises (rc != 0)."""
+    import torch
+    import torch.distributed as dist
+    import audio_algebra_b200 as aab
+    from audio_algebra_b200.training import MixerTrainer
+    from audio_algebra_b200.parallel import allreduce_mean_
+    from audio_algebra_b200.pca import RunningCovariance
+    out = {}
+
+    def rank_max_ms(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([sorted(ts)[len(ts) // 2]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- encoder sweep point (config 5): bf16 tcgen05 encoder, 256 chunks of 2^17 samples per rank ----
+    Be = 256
+    torch.manual_seed(0)                                   # the SAME frozen given model on every rank (a checkpoint in real use)
+    dvb = aab.DVAEWrapper(debug=False, compute_dtype="bf16").cuda()
+    xe = synth(Be, 99 + rank, dev)
+    ms = rank_max_ms(lambda: dvb.encode(xe), 5, 2)
+    out["encoder_ms"] = ms
+    out["encoder_audio_s_per_s"] = world * Be * CHUNK / SR / (ms * 1e-3)
+    out["encoder_tflops_per_gpu"] = Be * 68.17 / ms
+    del xe
+    # ---- data-parallel mixer training step (config 3 / 5): 2 stems of 512 x 2^16 per rank ----
+    Bm, Nm = 512, 65536
+    torch.manual_seed(2)                                   # same projector on every rank (train_aa_mixer_accel.py:51,479)
+    aa = aab.AudioAlgebra(64, 64).cuda()
+    tr = MixerTrainer(dvb.model, aa, total_steps=100)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)  # a different data shard per rank
+    stems = [torch.rand(Bm, 2, Nm, generator=g, device=dev) - 0.5 for _ in range(2)]
+    faders = [1.4630, -0.5718]
+    ms = rank_max_ms(lambda: tr.step(stems, faders), steps, 1)
+    out["train_step_ms"] = ms
+    out["train_audio_s_per_s"] = world * Bm * Nm / SR / (ms * 1e-3)
+    # parity: two more steps, keeping each rank's pre-all-reduce gradient of the last one
+    tr.keep_local_grad = True
+    tr.step(stems, faders)
+    tr.step(stems, faders)
+    torch.cuda.synchronize()
+    ok = True
+    detail = {}
+    if world > 1:
+        gp = [torch.empty_like(tr.flat) for _ in range(world)]
+        dist.all_gather(gp, tr.flat)
+        same_params = all(torch.equal(gp[0], q) for q in gp[1:])
+        gl = [torch.empty_like(tr.local_grad) for _ in range(world)]
+        dist.all_gather(gl, tr.local_grad)
+        mean = torch.stack([q.double() for q in gl]).mean(0)
+        rel = float(torch.linalg.vector_norm(tr.flat_grad.double() - mean) / torch.linalg.vector_norm(mean))
+        gr = [torch.empty_like(tr.flat_grad) for _ in range(world)]
+        dist.all_gather(gr, tr.flat_grad)
+        same_grads = all(torch.equal(gr[0], q) for q in gr[1:])
+        shards_differ = not torch.equal(gl[0], gl[1])     # the ranks really worked on different data
+        detail = {"params_bit_identical": same_params, "reduced_grad_bit_identical": same_grads,
+                  "reduced_grad_vs_mean_of_shards_rel_l2": rel, "local_grads_differ": shards_differ}
+        ok = same_params and same_grads and rel < 1e-5 and shards_differ
+    # ---- the collective alone: mean all-reduce of the flat 33 280-float gradient ----
+    n_ar = 50
+    buf = tr.flat_grad.clone()
+    for _ in range(5):
+        allreduce_mean_(buf)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_ar):
+        allreduce_mean_(buf)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n_ar], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["allreduce_us"] = 1e3 * float(t.item())
+    out["allreduce_bytes"] = buf.numel() * 4
+    del stems, tr, buf
+    # ---- PCA accumulation (config 4): 256 x [64, 512] latents per rank + the 4 097-float sum all-reduce ----
+    gy = torch.Generator(device=dev).manual_seed(31 + rank)
+    ys = torch.tanh(torch.randn(256, 64, Nm // 128, generator=gy, device=dev))
+    rc = RunningCovariance(64, dev)
+    out["pca_ms"] = rank_max_ms(lambda: rc.update(ys), 10, 2)
+    out["pca_GBps_per_gpu"] = ys.numel() * 4 / out["pca_ms"] / 1e6
+    rc2 = RunningCovariance(64, dev).update(ys)
+    local_num = rc2.cov_numerator.clone()
+    rc2.all_reduce()
+    torch.cuda.synchronize()
+    if world > 1:
+        gn = [torch.empty_like(local_num) for _ in range(world)]
+        dist.all_gather(gn, local_num)
+        tot = torch.stack([q.double() for q in gn]).sum(0)
+        rel = float(torch.linalg.vector_norm(rc2.cov_numerator.double() - tot) / torch.linalg.vector_norm(tot))
+        gr = [torch.empty_like(local_num) for _ in range(world)]
+        dist.all_gather(gr, rc2.cov_numerator)
+        same = all(torch.equal(gr[0], q) for q in gr[1:])
+        cnt_ok = int(rc2.count.item()) == world * 256 * (Nm // 128)
+        detail.update({"pca_numerator_bit_identical": same, "pca_sum_rel_l2": rel, "pca_count_ok": cnt_ok})
+        ok = ok and same and rel < 1e-5 and cnt_ok
+    out["dp_parity_ok"] = bool(ok)
+    out["dp_parity"] = detail
+    if not ok:
+        raise SystemExit(f"bench.py: cross-rank parity FAILED on rank {rank}: {detail}")
+    return out
+
+
+def host_copy_ceiling(dev, world, h2d_bytes, d2h_bytes, reps=3):
+    """What the host side can feed: every rank copies the e2e step's bytes pinned host -> device and device -> pinned host
+    CONCURRENTLY (two streams, no kernel); returns seconds per step, max over ranks.  e2e cannot beat this."""
+    import torch
+    import torch.distributed as dist
+    hi = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+    ho = torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
+    di = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    do = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for i in range(reps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            di.copy_(hi, non_blocking=True)
+        with torch.cuda.stream(s2):
+            ho.copy_(do, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    t = torch.tensor([best], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 64
-    for _ in range(max(args.warmup, 1)):
-        cpu_reference_rate(8, 1)
+    sample = BATCH          # the stated workload: all 256 chunks of configs[1] per step (about 0.3 s of CPU per step)
+    for _ in range(max(min(args.warmup, 2), 1)):
+        cpu_reference_rate(16, 1)
     import torch
     from oracle import aa_oracle as O
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -269,7 +417,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * mean_t, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} of the {BATCH} chunks per step (CPU arm, bounded)",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "chunk_samples": CHUNK, "sample": f"all {sample} chunks of the workload per step",
                    "path": "oracle restatement of the reference's CPU code path (torchaudio MelSpectrogram = torch.stft + "
                            "abs^2 + filterbank matmul), all host threads"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
@@ -305,13 +453,13 @@ def run_ours(args):
 
     mel = aab.MelSpectrogramAE(sample_rate=SR, n_fft=N_FFT, hop_length=HOP)
     x = synth(BATCH, 1234 + rank, dev)                       # 268 MB: larger than the 126 MB L2
+    sampler = ClockSampler(local) if rank == 0 else None     # returns once nvidia-smi has produced its first sample
     out = None
     for _ in range(max(args.warmup, 3)):
         out = mel.encode(x)
     barrier()
 
     # ---- device-resident throughput: K steps, one CUDA-event pair per step on the launch stream ----
-    sampler = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = lib.aa_launch_count()
     e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -330,7 +478,6 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     total_ms_max = float(t_max.item())
-    clocks = sampler.stop() if sampler else None
 
     # ---- end to end through the public API with host buffers (H2D + kernel + D2H inside the timed region) ----
     xh = x.cpu().pin_memory()
@@ -347,12 +494,20 @@ def run_ours(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = world * AUDIO_S_PER_STEP / float(t_e2e.item())
     assert oh.shape == out.shape
+    h2d_b, d2h_b = BATCH * 2 * CHUNK * 4, BATCH * 2 * N_MELS * (1 + CHUNK // HOP) * 4
+    t_copy = host_copy_ceiling(dev, world, h2d_b, d2h_b)
+    copy_ceiling = world * AUDIO_S_PER_STEP / t_copy
+    del xh, oh
+    dp = None
+    if not args.no_dp:
+        dp = run_dp(dev, world, rank)                        # raises on a cross-rank parity failure
+    clocks = sampler.stop() if sampler else None
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_ms = sum(kernel_ms) / len(kernel_ms)
         achieved = ALG_BYTES / (k_ms * 1e-3) / 1e9
-        cpu_val, cores, ts = cpu_reference_rate(32, 3) if world == 1 else (None, None, None)
+        cpu_val, cores, ts = cpu_reference_rate(BATCH, 3) if world == 1 else (None, None, None)
         line = {
             "metric": METRIC, "value": world * args.steps * AUDIO_S_PER_STEP / (total_ms_max * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
@@ -362,7 +517,10 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": BATCH * 2 * CHUNK * 4,
                     "d2h_bytes_per_step": BATCH * 2 * N_MELS * (1 + CHUNK // HOP) * 4,
                     "api": "MelSpectrogramAE.encode(pinned CPU tensor) -> aa_stft_mel_f32_host (chunked, copies overlapped)",
-                    "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None)},
+                    "host_copy_ceiling": copy_ceiling, "frac_of_host_copy_ceiling": e2e_val / copy_ceiling,
+                    "host_copy_GBps_per_rank": (h2d_b + d2h_b) / t_copy / 1e9,
+                    "host_copy_note": "every rank copies the step's H2D and D2H bytes concurrently from / to pinned memory, no kernel; max over ranks",
+                    "numa_nodes": numa_node_count(), "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "kernel": "stft2048_kernel<MEL>", "kernel_us": 1e3 * k_ms,
@@ -374,6 +532,14 @@ def run_ours(args):
                          "note": "latency / lock-step bound: FP32 pipe 47 %, issue 44 %, shared-memory pipe 70 % busy under ncu (DESIGN.md 4.1); not HBM bound"},
             "clocks": clocks,
         }
+        if dp is not None:
+            # top-level copies of the data-parallel figures (whole job, max over ranks) next to the nested record
+            for k in ("encoder_audio_s_per_s", "train_step_ms", "allreduce_us", "pca_ms", "dp_parity_ok"):
+                line[k] = dp[k]
+            line["dp"] = dict(dp, config={"encoder": "bf16 tcgen05 encoder, 256 x [2,131072] per rank",
+                                           "train_step": "MixerTrainer.step, 2 stems of 512 x [2,65536] per rank, mean all-reduce of the flat "
+                                                         "33 280-float gradient over NCCL (no collective at 1 GPU)",
+                                           "pca": "RunningCovariance.update on 256 x [64,512] per rank; sum all-reduce of 4 097 floats"})
         if world == 1 and not args.no_extras:
             try:
                 line["extras"] = run_extras(dev)
@@ -381,7 +547,7 @@ def run_ours(args):
                 line["extras"] = {"error": repr(e)}
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"32 of the {BATCH} chunks, best of 3 ({min(ts):.3f} s), oracle restatement of "
+                                    "sample": f"all {BATCH} chunks of the workload, best of 3 ({min(ts):.3f} s), oracle restatement of "
                                               f"the reference CPU path, torch {torch.__version__}"}
         print(json.dumps(line))
     if world > 1:
@@ -396,6 +562,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary (encoder / variants / training-step) measurements")
+    ap.add_argument("--no-dp", action="store_true", help="skip the data-parallel section (encoder, training step + all-reduce, PCA)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -404,7 +571,7 @@ def main():
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-extras"] if args.no_extras else [])
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-extras"] if args.no_extras else []) + (["--no-dp"] if args.no_dp else [])
         return subprocess.call(cmd)
     return run_ours(args)
 

@@ -239,7 +239,8 @@ def test_output_layouts_agree_and_match_the_reference_strides(aab, n_fft, hop, s
         y = m.encode(x)
         yc = m._run(x, mode, freq_major=True)
         assert yc.is_contiguous() and tuple(y.shape) == tuple(yc.shape)
-        assert torch.equal(y, yc)
+        # two kernels since round 2 (registers -> global for the frequency-minor layout, staged tiles for [F, T]): same values up to fp32 rounding
+        assert rel_l2(torch.view_as_real(y) if power is None else y, torch.view_as_real(yc) if power is None else yc) < 2e-6
         m.zero_pad = False
         ref = torchaudio.transforms.Spectrogram(n_fft=n_fft, hop_length=hop, power=power)(x.cpu())
         y2 = m.encode(x)

@@ -9,8 +9,10 @@ x = torch.rand(B, 2, n, device="cuda") - 0.5
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 res = {}
 for name, cls in [("mel", aab.MelSpectrogramAE), ("power", aab.MagSpectrogramAE), ("complex", aab.SpectrogramAE)]:
+    if name not in os.environ.get("MODES", "mel,power,complex").split(","):
+        continue
     kw = dict(sample_rate=48000) if name == "mel" else {}
-    m = cls(n_fft=2048, hop_length=512, **kw)
+    m = cls(n_fft=2048, hop_length=int(os.environ.get("HOP", 512)), center=os.environ.get("CENTER", "1") == "1", **kw)
     for _ in range(3):
         out = m.encode(x)
     torch.cuda.synchronize()
