@@ -39,6 +39,10 @@ _lib.register({
     "aa_cov_workspace_floats": (_i64, [_i64]),
     "aa_cov_accumulate_f32": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "aa_adam_step_f32": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _p]),
+    "aa_embed_block_fwd_f32": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _p]),
+    "aa_embed_block_bwd_f32": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "aa_batchnorm_fwd_f32": (_i, [_p, _i64, _i, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p]),
+    "aa_batchnorm_bwd_f32": (_i, [_p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _p]),
 })
 
 _RED_WS = int(lib.aa_reduce_workspace_floats())
@@ -238,26 +242,108 @@ class _ProjHalf(torch.autograd.Function):
         return (gx, None, None, None, *gws, *gbs)
 
 
+class _EmbedFn(torch.autograd.Function):
+    "one EmbedBlock on [n_tok, din] rows: Linear (+ exact-erf GELU) (+ residual) -> aa_embed_block_{fwd,bwd}_f32"
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, resid):
+        x, w = _f32c(x, "EmbedBlock input"), _f32c(w)
+        b = None if b is None else _f32c(b)
+        n_tok, din, dout = x.shape[0], w.shape[1], w.shape[0]
+        y = torch.empty((n_tok, dout), dtype=torch.float32, device=x.device)
+        pre = torch.empty_like(y)
+        with torch.cuda.device(x.device):
+            check(lib.aa_embed_block_fwd_f32(ptr(x), ptr(w), None if b is None else ptr(b), n_tok, din, dout, int(act), int(resid),
+                                             ptr(y), ptr(pre), stream_ptr()))
+        ctx.save_for_backward(x, w, pre)
+        ctx.cfg = (bool(act), bool(resid), b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, pre = ctx.saved_tensors
+        act, resid, has_b = ctx.cfg
+        gy = _f32c(gy)
+        n_tok, din, dout = x.shape[0], w.shape[1], w.shape[0]
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        need_w = ctx.needs_input_grad[1] or (has_b and ctx.needs_input_grad[2])
+        gw = torch.empty_like(w) if need_w else None
+        gb = torch.empty((dout,), dtype=torch.float32, device=x.device) if (need_w and has_b) else None
+        with torch.cuda.device(x.device):
+            check(lib.aa_embed_block_bwd_f32(ptr(x), ptr(w), ptr(pre), ptr(gy), n_tok, din, dout, int(act), int(resid),
+                                             None if gx is None else ptr(gx), None if gw is None else ptr(gw),
+                                             None if gb is None else ptr(gb), ptr(_ws(max(1, n_tok * dout), x.device)), stream_ptr()))
+        return gx, gw, gb, None, None
+
+
+class _BatchNormFn(torch.autograd.Function):
+    "nn.BatchNorm1d on [N, C] (training: batch statistics + running-statistics update; eval: running statistics)"
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, run_mean, run_var, training, momentum, eps):
+        x = _f32c(x, "BatchNorm input")
+        n, c = x.shape
+        y = torch.empty_like(x)
+        save = torch.empty((2, c), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.aa_batchnorm_fwd_f32(ptr(x), n, c, None if gamma is None else ptr(gamma), None if beta is None else ptr(beta),
+                                           None if run_mean is None else ptr(run_mean), None if run_var is None else ptr(run_var),
+                                           int(training), float(momentum), float(eps), ptr(y), ptr(save), stream_ptr()))
+        ctx.save_for_backward(x, gamma, save)
+        ctx.training = bool(training)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, save = ctx.saved_tensors
+        gy = _f32c(gy)
+        n, c = x.shape
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gg = torch.empty((c,), dtype=torch.float32, device=x.device)
+        gb = torch.empty((c,), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.aa_batchnorm_bwd_f32(ptr(x), ptr(gy), n, c, None if gamma is None else ptr(gamma), ptr(save), int(ctx.training),
+                                           None if gx is None else ptr(gx), ptr(gg), ptr(gb), stream_ptr()))
+        return gx, (gg if gamma is not None else None), (gb if gamma is not None else None), None, None, None, None, None
+
+
 class EmbedBlock(nn.Module):
-    """Parameter holder with the reference's layout (aa_mixer.py:205-221): `lin` = nn.Linear(in, out).
-    The arithmetic of four consecutive blocks is fused in AudioAlgebra.encode/decode; calling a single
-    block directly is not part of the accelerated path."""
+    """The reference's EmbedBlock (aa_mixer.py:205-221): `lin` = nn.Linear(in, out); y = lin(x); y = act(y); y = bn(y) (use_bn);
+    x + y iff resid and in == out.  Callable on its own ([..., in_dims] rows -> aa_embed_block_fwd_f32, autograd included);
+    inside AudioAlgebra four consecutive blocks run as ONE fused kernel per half instead.  act must be nn.GELU() (exact erf)
+    or None.  use_bn: nn.BatchNorm1d(out_dims) applied to 2-D [N, out_dims] activations, the only rank for which the
+    reference's placement of the layer is well formed (with [B, T, C] input BatchNorm1d would read T as the channel axis)."""
 
     def __init__(self, in_dims: int, out_dims: int, act=nn.GELU(), resid=True, use_bn=False, requires_grad=True, **kwargs) -> None:
         super().__init__()
-        if use_bn:
-            raise NotImplementedError("use_bn=True is not supported by the fused projector")
         if act is not None and not (isinstance(act, nn.GELU) and getattr(act, "approximate", "none") == "none"):
-            raise NotImplementedError("the fused projector implements act=nn.GELU() (exact erf) or act=None")
+            raise NotImplementedError("EmbedBlock implements act=nn.GELU() (exact erf) or act=None")
         self.in_dims, self.out_dims, self.act, self.resid = in_dims, out_dims, act, resid
         self.lin = nn.Linear(in_dims, out_dims, **kwargs)
-        self.bn = None
+        self.bn = nn.BatchNorm1d(out_dims) if use_bn else None   # parameter / running-statistics holder; arithmetic in _BatchNormFn
         if requires_grad == False:  # noqa: E712  (reference spelling)
             self.lin.weight.requires_grad = False
             self.lin.bias.requires_grad = False
 
     def forward(self, xin: Tensor) -> Tensor:
-        raise NotImplementedError("EmbedBlock is evaluated inside AudioAlgebra.encode/decode (fused kernel)")
+        _lib.require_cuda(xin, "EmbedBlock input")
+        assert xin.shape[-1] == self.in_dims, f"expected [..., {self.in_dims}], got {tuple(xin.shape)}"
+        add_resid = self.resid and self.in_dims == self.out_dims
+        rows = xin.reshape(-1, self.in_dims)
+        if self.bn is None:
+            y = _EmbedFn.apply(rows, self.lin.weight, self.lin.bias, self.act is not None, add_resid)
+            return y.reshape(*xin.shape[:-1], self.out_dims)
+        if xin.dim() != 2:
+            raise ValueError(f"EmbedBlock(use_bn=True): BatchNorm1d({self.out_dims}) needs [N, {self.out_dims}] activations, got input "
+                             f"{tuple(xin.shape)} (the reference's BatchNorm1d would take axis 1 of a 3-D tensor as channels)")
+        y = _EmbedFn.apply(rows, self.lin.weight, self.lin.bias, self.act is not None, False)
+        bn = self.bn
+        training = bn.training or bn.running_mean is None
+        if bn.training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        y = _BatchNormFn.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, momentum, bn.eps)
+        return _lincomb_ad([xin, y], [1.0, 1.0]) if add_resid else y
 
 
 class AudioAlgebra(nn.Module):
@@ -286,6 +372,9 @@ class AudioAlgebra(nn.Module):
         )
 
     def _half(self, seq, xin):
+        if any(blk.bn is not None for blk in seq):   # use_bn: block by block, exactly the reference's data flow (aa_mixer.py:252-254)
+            x = seq(xin.transpose(1, 2)).transpose(1, 2)
+            return _lincomb_ad([x, xin], [1.0, 1.0]) if self.resid else x
         ws = [blk.lin.weight for blk in seq]
         bs = [blk.lin.bias for blk in seq]
         return _ProjHalf.apply(xin, self.resid, self.dims, self.hidden_dims, *ws, *bs)

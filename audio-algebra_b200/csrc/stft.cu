@@ -1289,11 +1289,11 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
   a.mel_w4 = p->d_mel_w4; a.out = out; a.out_tf = out_tf;
   a.wav_aligned16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0) ? 1 : 0;
   const bool big_out = rows * (int64_t)std::max(p->n_freq, p->n_mels) * n_frames >= (1LL << 31);
-  static const int v2_mode = getenv("AA_STFT_V2") ? atoi(getenv("AA_STFT_V2")) : 1;       // 0: v1 kernel only
+  const int v2_mode = getenv("AA_STFT_V2") ? atoi(getenv("AA_STFT_V2")) : 1;       // 0: v1 kernel only
   static const int v2_nbuf = getenv("AA_STFT_NBUF") ? atoi(getenv("AA_STFT_NBUF")) : 1;     // sample ring depth wanted (1 or 2)
   // mel: the v2 kernel's banded walk is correct but still slower end to end than the v1 tile kernel (393 vs 375 us on the headline
   // workload: every warp walks right after the P-line rendezvous, so the walk's latency is not hidden) -- opt in with AA_STFT_V2_MEL=1
-  static const bool v2_mel = getenv("AA_STFT_V2_MEL") != nullptr && atoi(getenv("AA_STFT_V2_MEL")) != 0;
+  const bool v2_mel = getenv("AA_STFT_V2_MEL") != nullptr && atoi(getenv("AA_STFT_V2_MEL")) != 0;
   if (p->fast && !big_out && v2_mode && rows < (1LL << 30) && n_pad < (1LL << 30) &&
       ((mode == MODE_MEL && p->v2_mel_ok && v2_mel) || (mode != MODE_MEL && out_tf))) {
     const int groups_len = mode == MODE_MEL ? p->v2_groups_len : 1;

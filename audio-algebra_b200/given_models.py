@@ -277,14 +277,13 @@ class MagSpectrogramAE(_StftFrontEnd):
 
 
 class MagDPhaseSpectrogramAE(_StftFrontEnd):
-    """Magnitude + phase-change spectrogram (given_models.py:192-254), use_cos=False branch.  Like the
-    reference, encode() is defined for unbatched [c, N] input and returns [2c, F, T]."""
+    """Magnitude + phase-change spectrogram (given_models.py:192-254): both the phase-difference branch and the use_cos
+    (acos of the normalised dot product) branch, plus the `debug` phase wrap.  Like the reference, encode() is defined for
+    unbatched [c, N] input and returns [2c, F, T]."""
 
     def __init__(self, n_fft=1024, hop_length=256, center=True, init='true', use_cos=False, debug=False,
                  cheat=False, **kwargs):
         super().__init__(n_fft, hop_length, center, kwargs)
-        if use_cos:
-            raise NotImplementedError("use_cos=True (acos phase differences) is not on the accelerated path")
         self.use_cos, self.cheat, self.debug, self.init = use_cos, cheat, debug, init
         self.pi = 3.141592653589
 
@@ -297,7 +296,7 @@ class MagDPhaseSpectrogramAE(_StftFrontEnd):
         c, f, t = spec.shape
         out = torch.empty((2 * c, f, t), dtype=torch.float32, device=spec.device)
         with torch.cuda.device(spec.device):
-            check(lib.aa_magdphase_f32(ptr(spec), c, f, t, ptr(out), stream_ptr()))
+            check(lib.aa_magdphase_ex_f32(ptr(spec), c, f, t, int(bool(self.use_cos)), int(bool(self.debug)), ptr(out), stream_ptr()))
         return out.cpu() if on_cpu else out
 
 

@@ -116,6 +116,46 @@ int aa_latent_unary_f32(int op, const float* z, float* out, int64_t b, int64_t c
 int aa_effect_transfer_f32(const float* emb, int64_t b, const float* wet, const float* dry, int64_t bw,
                            int64_t ct, float* out, void* stream);
 
+/* --- remaining Destructo.ipynb cell 22 operations (csrc/latent_ext.cu); z, out are [B][C][T] f32 --------------------------- */
+/* "wavy": out = z * vec[t]; the caller passes vec = cos(linspace(0, 4*6.28, T)) computed as the notebook computes it */
+int aa_latent_mul_time_f32(const float* z, const float* vec, float* out, int64_t b, int64_t c, int64_t t, void* stream);
+/* "flippy": out = z + flip(z, -1) (not in place) */
+int aa_latent_add_flip_time_f32(const float* z, float* out, int64_t b, int64_t c, int64_t t, void* stream);
+/* "kill_half": out = z with channels [c0, c1) zeroed (the notebook: z[:, 33:-1, :] = 0) */
+int aa_latent_zero_channels_f32(const float* z, float* out, int64_t b, int64_t c, int64_t t, int64_t c0, int64_t c1, void* stream);
+/* "call_and_response" / "hurt_drums": out = a*x + (b*z) * (2*u - 1) with u = torch.rand_like(z) supplied by the caller
+ * (x = z, a = -1, b = rand_fac  /  x = embeddings, a = 1 - rand_fac, b = rand_fac) */
+int aa_latent_randmix_f32(const float* x, const float* z, const float* u, float a, float b, float* out, int64_t n, void* stream);
+/* "reverb_time": for i in range(T): z = z + coef[i] * shift_right(z, i+1) on the updated z; coef[i] = (float)exp(-i/reverb_time);
+ * z, out [rows][T] */
+int aa_latent_reverb_f32(const float* z, const float* coef, float* out, int64_t rows, int64_t t, void* stream);
+/* Destructo.ipynb cell 49 with unequal lengths: diff = wet - dry [Bw][C][t_diff] is left-padded with zeros (F.pad(diff,
+ * (length_difference, 0, ...))) or truncated to t_emb, averaged over Bw, and added to every emb[b] ([B][C][t_emb]). */
+int aa_effect_transfer_ex_f32(const float* emb, int64_t b, int64_t c, int64_t t_emb, const float* wet, const float* dry,
+                              int64_t bw, int64_t t_diff, float* out, void* stream);
+/* cell 49 time_avg=True: out[row] = mean_t(wet[row][t] - dry[row][t]); then torch broadcasting of that 2-D tensor [d0][d1]
+ * against [B][C][T] (d0 in {1, C}, d1 in {1, T}; anything else is the broadcasting error the notebook would raise) */
+int aa_latent_row_mean_diff_f32(const float* wet, const float* dry, int64_t rows, int64_t t, float* out, void* stream);
+int aa_latent_add_bcast2_f32(const float* z, int64_t b, int64_t c, int64_t t, const float* d, int64_t d0, int64_t d1, float* out,
+                             void* stream);
+/* MagDPhaseSpectrogramAE.encode with its use_cos (acos of the clipped normalised dot product of consecutive frames,
+ * given_models.py:218-225) and debug (theta < 0 -> theta + 2 pi before differencing, :215) branches */
+int aa_magdphase_ex_f32(const float* spec, int64_t c, int64_t n_freq, int64_t n_frames, int use_cos, int wrap_theta, float* out,
+                        void* stream);
+/* Standalone EmbedBlock (aa_mixer.py:205-221) on [n_tok][din] rows: y = Linear(x) (+ exact-erf GELU if act) (+ x if resid);
+ * pre_out (optional) keeps Linear(x) for the backward.  BatchNorm1d(out_dims) of the use_bn variant is the separate pair below
+ * (the reference applies it to [N, C] inputs -- the only rank its BatchNorm1d accepts there). */
+int aa_embed_block_fwd_f32(const float* x, const float* w, const float* bias, int64_t n_tok, int din, int dout, int act, int resid,
+                           float* y, float* pre_out, void* stream);
+/* scratch: n_tok * dout floats; gx / gw / gb may be NULL (gb needs gw) */
+int aa_embed_block_bwd_f32(const float* x, const float* w, const float* pre, const float* gy, int64_t n_tok, int din, int dout,
+                           int act, int resid, float* gx, float* gw, float* gb, float* scratch, void* stream);
+/* x, y [n][c]; save [2][c] (mean, rstd); training updates run_mean / run_var with `momentum` (unbiased variance) */
+int aa_batchnorm_fwd_f32(const float* x, int64_t n, int c, const float* gamma, const float* beta, float* run_mean, float* run_var,
+                         int training, float momentum, float eps, float* y, float* save, void* stream);
+int aa_batchnorm_bwd_f32(const float* x, const float* gy, int64_t n, int c, const float* gamma, const float* save, int training,
+                         float* gx, float* ggamma, float* gbeta, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Losses (aa_mixer.py:344-364; L2-hinge variant train_aa_effects.py:42-46).
  * z is [B][D] f32 (D = C*T flattened features), the batch dimension is the statistics dimension.

@@ -81,6 +81,8 @@ def main():
     x_mdp = synth((2, 4096), 15)
     d["x_mdp"] = x_mdp.numpy()
     d["magdphase"] = gm.MagDPhaseSpectrogramAE().encode(x_mdp).numpy()
+    d["magdphase_use_cos"] = gm.MagDPhaseSpectrogramAE(use_cos=True).encode(x_mdp).numpy()
+    d["magdphase_debug"] = gm.MagDPhaseSpectrogramAE(debug=True).encode(x_mdp).numpy()
     # mel filterbank itself
     import torchaudio
     d["fb_2048_48k_128"] = torchaudio.functional.melscale_fbanks(1025, 0.0, 24000.0, 128, 48000).numpy()
@@ -119,6 +121,25 @@ def main():
     for k, p in aa.named_parameters():
         d["grad." + k] = p.grad.numpy()
     torch.set_grad_enabled(False)
+    # standalone EmbedBlock (aa_mixer.py:205-221): 3-D rows without BN; 2-D rows with BatchNorm1d in training then eval mode
+    torch.manual_seed(5)
+    blk = mx.EmbedBlock(64, 64)
+    xb = torch.randn(3, 7, 64)
+    d["blk_w"], d["blk_b"], d["blk_x"], d["blk_y"] = blk.lin.weight.numpy(), blk.lin.bias.numpy(), xb.numpy(), blk(xb).numpy()
+    blk2 = mx.EmbedBlock(16, 24, act=None)           # no residual (in != out), no activation
+    xb2 = torch.randn(5, 16)
+    d["blk2_w"], d["blk2_b"], d["blk2_x"], d["blk2_y"] = blk2.lin.weight.numpy(), blk2.lin.bias.numpy(), xb2.numpy(), blk2(xb2).numpy()
+    blk3 = mx.EmbedBlock(8, 8, use_bn=True)
+    blk3.bn.weight.data = torch.rand(8) + 0.5
+    blk3.bn.bias.data = torch.randn(8) * 0.1
+    xb3 = torch.randn(10, 8)
+    d["blk3_w"], d["blk3_b"], d["blk3_bn_w"], d["blk3_bn_b"], d["blk3_x"] = (blk3.lin.weight.numpy(), blk3.lin.bias.numpy(),
+                                                                               blk3.bn.weight.numpy().copy(), blk3.bn.bias.numpy().copy(), xb3.numpy())
+    blk3.train()
+    d["blk3_y_train"] = blk3(xb3).numpy()
+    d["blk3_run_mean"], d["blk3_run_var"] = blk3.bn.running_mean.numpy().copy(), blk3.bn.running_var.numpy().copy()
+    blk3.eval()
+    d["blk3_y_eval"] = blk3(xb3).numpy()
     np.savez_compressed(os.path.join(OUT, "projector.npz"), **d)
 
     # ---------------- losses ----------------

@@ -69,8 +69,10 @@ def test_constructor_contracts():
         aab.MelSpectrogramAE(bogus_kwarg=1)
     aa = aab.AudioAlgebra(dims=64, hidden_dims=64)
     assert sum(p.numel() for p in aa.parameters()) == 33280   # 33 280 parameters
+    bn = aab.AudioAlgebra(dims=64, hidden_dims=64, use_bn=True)   # constructible, same extra keys as the reference's BatchNorm1d blocks
+    assert "encoder.0.bn.running_mean" in bn.state_dict() and isinstance(bn.encoder[0].bn, torch.nn.BatchNorm1d)
     with pytest.raises(NotImplementedError):
-        aab.AudioAlgebra(dims=64, hidden_dims=64, use_bn=True)
+        aab.EmbedBlock(4, 4, act=torch.nn.ReLU())
 
 
 def test_onecycle_schedule_matches_torch():

@@ -183,6 +183,95 @@ def test_latent_ops(aab):
     assert rel_l2(aab.latent_lincomb([t.cuda()[1:] for t in odd], [2.0, 0.5]), 2 * odd[0][1:].double() + 0.5 * odd[1][1:].double()) < 1e-6
 
 
+def test_destructo_cell22_ops(aab):
+    "the remaining Destructo.ipynb cell 22 operations against the oracle's restatement of the cell"
+    O = _oracle()
+    from audio_algebra_b200 import latent_ops as L
+    g = torch.Generator().manual_seed(9)
+    z = torch.tanh(torch.randn(3, 64, 80, generator=g))
+    zc = z.cuda()
+    assert torch.equal(L.wavy(zc).cpu(), O.destructo_wavy(z))                    # fp32 modulation built on the CPU, one multiply
+    assert torch.equal(L.flippy(zc).cpu(), O.destructo_flippy(z))
+    assert torch.equal(L.kill_half(zc).cpu(), O.destructo_kill_half(z))
+    assert torch.equal(L.big_changes(zc).cpu(), 2 * z)
+    for rt in (2.5, 40.0):
+        assert torch.equal(L.reverb_time(zc, rt).cpu(), O.destructo_reverb(z, rt))  # same unfused fp32 operations in the same order
+    assert torch.equal(L.reverb_time(zc, 0).cpu(), z)
+    zl = torch.tanh(torch.randn(1, 64, 1024, generator=g))                       # config-1 latent length
+    assert rel_l2(L.reverb_time(zl.cuda(), 100.0), O.destructo_reverb(zl.double(), 100.0)) < 1e-5
+    u = torch.rand(z.shape, generator=g)
+    assert torch.equal(L.call_and_response(zc, 0.5, u=u.cuda()).cpu(), O.destructo_call_and_response(z, u, 0.5))
+    emb = torch.tanh(torch.randn(3, 64, 80, generator=g))
+    assert rel_l2(L.hurt_drums(emb.cuda(), zc, 0.3, u=u.cuda()), O.destructo_hurt_drums(emb.double(), z.double(), u.double(), 0.3)) < 1e-6
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    a = L.call_and_response(zc, 0.5, generator=gen)
+    gen.manual_seed(1)
+    b = L.call_and_response(zc, 0.5, generator=gen)
+    assert torch.equal(a, b) and not torch.equal(a, -zc)
+
+
+def test_effect_transfer_cell49_variants(aab):
+    "cell 49: left zero-padding / truncation of the wet-dry difference to the embedding length, and the time_avg branch"
+    O = _oracle()
+    from audio_algebra_b200 import latent_ops as L
+    g = torch.Generator().manual_seed(10)
+    z = torch.tanh(torch.randn(4, 64, 50, generator=g))
+    for td in (50, 37, 64):
+        wet, dry = torch.randn(5, 64, td, generator=g), torch.randn(5, 64, td, generator=g)
+        assert rel_l2(L.effect_transfer(z.cuda(), wet.cuda(), dry.cuda()), O.effect_transfer(z.double(), wet.double(), dry.double())) < 1e-6
+    wet, dry = torch.randn(5, 64, 50, generator=g), torch.randn(5, 64, 50, generator=g)
+    with pytest.raises(RuntimeError):                                            # [5, 64] vs [4, 64, 50]: the notebook's own broadcasting error
+        L.effect_transfer(z.cuda(), wet.cuda(), dry.cuda(), time_avg=True)
+    z2 = torch.tanh(torch.randn(3, 8, 16, generator=g))                          # a shape for which `z + diff.mean(-1)` is defined
+    wet2, dry2 = torch.randn(8, 16, 21, generator=g), torch.randn(8, 16, 21, generator=g)
+    assert rel_l2(L.effect_transfer(z2.cuda(), wet2.cuda(), dry2.cuda(), time_avg=True),
+                  O.effect_transfer(z2.double(), wet2.double(), dry2.double(), time_avg=True)) < 1e-6
+
+
+def test_embed_block_standalone_golden(aab, golden):
+    "EmbedBlock.forward on its own (aa_mixer.py:216-221) against the reference's outputs, gradients against fp64 autograd"
+    O = _oracle()
+    g = golden("projector")
+    blk = aab.EmbedBlock(64, 64)
+    blk.load_state_dict({"lin.weight": T(g["blk_w"]), "lin.bias": T(g["blk_b"])})
+    blk = blk.cuda()
+    x = T(g["blk_x"]).cuda().requires_grad_(True)
+    y = blk(x)
+    assert tuple(y.shape) == (3, 7, 64) and rel_l2(y, g["blk_y"]) < 1e-5
+    gy = torch.randn(3, 7, 64, generator=torch.Generator().manual_seed(1))
+    y.backward(gy.cuda())
+    xd = T(g["blk_x"]).double().requires_grad_(True)
+    wd, bd = T(g["blk_w"]).double().requires_grad_(True), T(g["blk_b"]).double().requires_grad_(True)
+    O.embed_block(xd, wd, bd, act=True, resid=True).backward(gy.double())
+    assert rel_l2(x.grad, xd.grad) < 1e-5 and rel_l2(blk.lin.weight.grad, wd.grad) < 1e-5 and rel_l2(blk.lin.bias.grad, bd.grad) < 1e-5
+    blk2 = aab.EmbedBlock(16, 24, act=None)
+    blk2.load_state_dict({"lin.weight": T(g["blk2_w"]), "lin.bias": T(g["blk2_b"])})
+    assert rel_l2(blk2.cuda()(T(g["blk2_x"]).cuda()), g["blk2_y"]) < 1e-5
+    # use_bn: BatchNorm1d on [N, C] rows, training (batch statistics, running statistics updated) then eval
+    blk3 = aab.EmbedBlock(8, 8, use_bn=True)
+    blk3.load_state_dict({"lin.weight": T(g["blk3_w"]), "lin.bias": T(g["blk3_b"]), "bn.weight": T(g["blk3_bn_w"]), "bn.bias": T(g["blk3_bn_b"])},
+                         strict=False)
+    blk3 = blk3.cuda().train()
+    x3 = T(g["blk3_x"]).cuda().requires_grad_(True)
+    y3 = blk3(x3)
+    assert rel_l2(y3, g["blk3_y_train"]) < 1e-5
+    assert rel_l2(blk3.bn.running_mean, g["blk3_run_mean"]) < 1e-5 and rel_l2(blk3.bn.running_var, g["blk3_run_var"]) < 1e-5
+    y3.square().sum().backward()
+    ref = torch.nn.Sequential()   # fp64 torch restatement of the block for the gradient check
+    lin, bn = torch.nn.Linear(8, 8).double(), torch.nn.BatchNorm1d(8).double()
+    lin.load_state_dict({"weight": T(g["blk3_w"]).double(), "bias": T(g["blk3_b"]).double()})
+    bn.weight.data, bn.bias.data = T(g["blk3_bn_w"]).double(), T(g["blk3_bn_b"]).double()
+    xr = T(g["blk3_x"]).double().requires_grad_(True)
+    (xr + bn(torch.nn.functional.gelu(lin(xr)))).square().sum().backward()
+    assert rel_l2(x3.grad, xr.grad) < 1e-4 and rel_l2(blk3.lin.weight.grad, lin.weight.grad) < 1e-4
+    assert rel_l2(blk3.bn.weight.grad, bn.weight.grad) < 1e-4 and rel_l2(blk3.bn.bias.grad, bn.bias.grad) < 1e-4
+    assert rel_l2(blk3.eval()(T(g["blk3_x"]).cuda()), g["blk3_y_eval"]) < 1e-5
+    with pytest.raises(ValueError):
+        blk3(torch.zeros(2, 3, 8, device="cuda"))
+    with pytest.raises(ValueError):                       # AudioAlgebra(use_bn=True) walks the blocks one by one and hits the same wall
+        aab.AudioAlgebra(8, 8, use_bn=True).cuda()(torch.zeros(2, 8, 5, device="cuda"))
+
+
 class _ToyGiven(torch.nn.Module):
     def __init__(self, w):
         super().__init__()

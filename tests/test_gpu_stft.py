@@ -87,6 +87,24 @@ def test_magdphase(aab, golden):
     assert d[strong].abs().max() < 2e-3
 
 
+@pytest.mark.parametrize("key,kw", [("magdphase_use_cos", dict(use_cos=True)), ("magdphase_debug", dict(debug=True))])
+def test_magdphase_use_cos_and_debug_branches(aab, golden, key, kw):
+    g = golden("stft")
+    out = aab.MagDPhaseSpectrogramAE(**kw).encode(T(g["x_mdp"]).cuda()).cpu().double()
+    ref = T(g[key]).double()
+    c = ref.shape[0] // 2
+    assert tuple(out.shape) == tuple(ref.shape) and rel_l2(out[:c], ref[:c]) < TOL
+    strong = ref[:c] > 1e-2 * ref[:c].max()
+    if "use_cos" in kw:   # acos is ill-conditioned near +-1: compare the cosines on bins that carry energy; column 0 holds theta
+        assert (torch.cos(out[c:])[..., 1:][strong[..., 1:]] - torch.cos(ref[c:])[..., 1:][strong[..., 1:]]).abs().max() < 2e-3
+        d0 = (out[c:, :, 0] - ref[c:, :, 0] + np.pi) % (2 * np.pi) - np.pi
+        assert d0[strong[..., 0]].abs().max() < 2e-3
+    else:
+        d = (out[c:] - ref[c:] + np.pi) % (2 * np.pi) - np.pi
+        assert d[strong].abs().max() < 2e-3
+        assert out[c:].min() >= 0          # debug: phases wrapped into [0, 2 pi) before differencing, differences wrapped too
+
+
 @pytest.mark.parametrize("n_fft,hop,n", [(2048, 512, 16384), (2048, 256, 8192), (2048, 1024, 8192), (2048, 500, 9000),
                                          (512, 128, 4096), (4096, 1024, 16384), (256, 64, 1000), (2048, 2048, 8192)])
 def test_oracle_sweep(aab, n_fft, hop, n):
@@ -246,3 +264,28 @@ def test_output_layouts_agree_and_match_the_reference_strides(aab, n_fft, hop, s
         y2 = m.encode(x)
         assert tuple(y2.shape) == tuple(ref.shape) and y2.stride()[-2:] == ref.stride()[-2:] == (1, n_fft // 2 + 1)
         assert rel_l2(torch.view_as_real(y2) if power is None else y2, torch.view_as_real(ref) if power is None else ref) < 1e-4
+
+
+@pytest.mark.parametrize("hop,n,rows", [(512, 131072, (2, 2)), (512, 20000, (3, 1)), (256, 16384, (1, 2)), (1024, 40000, (2, 2)), (500, 9000, (1, 2))])
+def test_v2_kernel_banded_mel_and_v1_kernels_agree_with_the_oracle(aab, monkeypatch, hop, n, rows):
+    """The decoupled-warp n_fft = 2048 kernel (stft2048_v2_kernel) serves the frequency-minor complex / power outputs by default
+    and the mel output when AA_STFT_V2_MEL=1; the v1 tile kernel serves the rest.  Both paths, every mode, against the float64
+    oracle: multi-tile rows (131072 samples = 22 tiles of 12 frames), odd row counts (no partner row), non-power-of-two lengths
+    (zero_pad_po2 tail inside a frame), hop = 1024 (sample ring depth 1) and a hop that is not a multiple of 4 (generic kernel)."""
+    from oracle import aa_oracle as O
+    g = torch.Generator().manual_seed(hop + n)
+    x = torch.rand(*rows, n, generator=g) - 0.5
+    ref = O.mel_spectrogram(x, 48000, 2048, hop)
+    for v2_mel in ("0", "1"):
+        monkeypatch.setenv("AA_STFT_V2_MEL", v2_mel)
+        y = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=hop).encode(x.cuda())
+        assert tuple(y.shape) == tuple(ref.shape)
+        assert rel_l2(y, ref) < 1e-5, f"mel, AA_STFT_V2_MEL={v2_mel}"
+    refp = O.power_spectrogram(x, 2048, hop) if hasattr(O, "power_spectrogram") else None
+    for v2 in ("0", "1"):
+        monkeypatch.setenv("AA_STFT_V2", v2)
+        yp = aab.MagSpectrogramAE(n_fft=2048, hop_length=hop).encode(x.cuda())
+        yc = aab.SpectrogramAE(n_fft=2048, hop_length=hop).encode(x.cuda())
+        assert rel_l2(yc.abs() ** 2, yp) < 1e-5
+        if refp is not None:
+            assert rel_l2(yp, refp) < 1e-5, f"power, AA_STFT_V2={v2}"

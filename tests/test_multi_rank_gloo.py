@@ -39,7 +39,11 @@ def test_two_rank_gloo():
     sys.path.insert(0, ROOT)
     from oracle import aa_oracle as O
     from audio_algebra_b200.parallel import shard_range
-    world, port = 2, 29533
+    import socket
+    with socket.socket() as sk:          # a free port (a fixed one can still be in TIME_WAIT from an earlier run)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
