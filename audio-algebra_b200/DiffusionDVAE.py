@@ -5,7 +5,10 @@ audio_algebra/DiffusionDVAE.py:98-160): constructor arguments, `encode` (eval: e
 `SoundStreamXLEncoder` restates the third-party `autoencoders.soundstream.SoundStreamXLEncoder`
 (audio-diffusion, un-pinned git dependency, source absent from the reference tree): architecture per
 SURVEY.md Appendix A -- PARITY UNPINNED upstream; only the [B,2,N] -> [B,64,N/128] shape is pinned
-(Destructo.ipynb cell 17).  Diffusion decoder / sampler, PQMF and Memcodes branches are out of scope and raise.
+(Destructo.ipynb cell 17).  `PQMF`, `Memcodes` and `ResidualMemcodes` restate the other three third-party modules on
+encode_it's route (`diffusion.pqmf.PQMF`, `nwt_pytorch.Memcodes`, `dvae.residual_memcodes.ResidualMemcodes`), equally
+unpinned and off at the reference defaults (pqmf_bands = 1, num_quantizers = 0).  The diffusion decoder / sampler is out
+of scope and raises.
 """
 import ctypes as C
 import math
@@ -18,7 +21,7 @@ from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 from .aa_mixer import _ptr_array, _f32c
 
-__all__ = ['SoundStreamXLEncoder', 'DiffusionDVAE']
+__all__ = ['SoundStreamXLEncoder', 'DiffusionDVAE', 'PQMF', 'Memcodes', 'ResidualMemcodes', 'load_dvae_encoder_checkpoint']
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pp = C.POINTER(C.c_void_p)
@@ -38,6 +41,9 @@ _lib.register({
     "aa_encoder_out_length": (_i, [_p, _i64, C.POINTER(_i64)]),
     "aa_encoder_workspace_bytes": (_i64, [_p, _i64, _i64, _i]),
     "aa_encoder_forward": (_i, [_p, _pp, C.POINTER(_f), _i, _i64, _i64, _i, _i, _p, _p, _p]),
+    "aa_pqmf_analysis_f32": (_i, [_p, _i64, _i64, _p, _i, _i, _p, _p]),
+    "aa_memcodes_kv_f32": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "aa_memcodes_quantize_f32": (_i, [_p, _i64, _i, _i, _i64, _p, _p, _i, _f, _p, _p, _p, _i, _p, _p]),
 })
 
 DTYPES = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "tf32x3": 2, "3xtf32": 2, "fp32_cuda_cores": 3}
@@ -121,7 +127,7 @@ class SoundStreamXLEncoder(nn.Module):
             H.h[dev], H.versions[dev] = h, None
         h = H.h[dev]
         convs = self.flat_convs()
-        ver = tuple((c.weight._version, c.bias._version, c.weight.data_ptr()) for c in convs)
+        ver = tuple((c.weight._version, c.bias._version, c.weight.data_ptr(), c.bias.data_ptr()) for c in convs)
         if H.versions[dev] != ver:
             for i, c in enumerate(convs):
                 _lib.require_cuda(c.weight, "encoder weights")
@@ -147,6 +153,8 @@ class SoundStreamXLEncoder(nn.Module):
         b, n = x0.shape[0], x0.shape[2]
         dev = _lib.ensure_device(x0.device)
         dt = DTYPES[self.compute_dtype]
+        if self.in_channels not in (1, 2):   # PQMF front-end (2 * bands input channels): the tensor-core first-layer kernels are
+            dt = DTYPES["fp32_cuda_cores"]   # built for mono / stereo input; the generic fp32 kernel takes any layer table
         with torch.cuda.device(dev):
             h = self._handle(dev)
             y = torch.empty((b, self.latent_dim, self.out_length(n)), dtype=torch.float32, device=x0.device)
@@ -168,6 +176,196 @@ class SoundStreamXLEncoder(nn.Module):
         return y.squeeze(0) if squeeze else y
 
 
+# ---------------------------------------------------------------------------------------------------
+# PQMF analysis front-end (restated `diffusion.pqmf.PQMF`, the RAVE pseudo-QMF bank; unpinned upstream)
+# ---------------------------------------------------------------------------------------------------
+
+def _kaiser_filter(wc, atten, n=None):
+    import numpy as np
+    from scipy.signal import firwin, kaiserord
+    n_, beta = kaiserord(atten, wc / np.pi)
+    n_ = 2 * (n_ // 2) + 1
+    n = n if n is not None else n_
+    return firwin(n, wc, window=("kaiser", beta), scale=False, fs=2 * np.pi)
+
+
+def _pqmf_prototype(atten, m, n=None):
+    "low-pass prototype whose cutoff minimises the reconstruction error of the m-band cosine-modulated bank"
+    import numpy as np
+    from scipy.optimize import fmin
+
+    def loss(wc):
+        h = _kaiser_filter(float(np.atleast_1d(wc)[0]), atten, n)
+        g = np.convolve(h, h[::-1])
+        g = abs(g[g.shape[-1] // 2::2 * m][1:])
+        return np.max(g)
+
+    wc = fmin(loss, 1 / m, disp=0)[0]
+    return _kaiser_filter(wc, atten, n)
+
+
+def _center_pad_next_pow_2(x):
+    import numpy as np
+    nxt = 2 ** math.ceil(math.log2(x.shape[-1]))
+    pad = nxt - x.shape[-1]
+    return np.pad(x, [(0, 0)] * (x.ndim - 1) + [(pad // 2, pad // 2 + int(pad % 2))])
+
+
+def pqmf_filterbank(attenuation, n_band):
+    "hk [n_band][taps] float64: 2 h cos((2k+1) pi/(2M) t + (-1)^k pi/4), taps padded to a power of two (as the polyphase form wants)"
+    import numpy as np
+    h = _pqmf_prototype(attenuation, n_band)          # odd length, symmetric about its centre tap
+    k = np.arange(n_band).reshape(-1, 1)
+    n = h.shape[-1]
+    t = np.arange(-(n // 2), n // 2 + 1)
+    p = (-1.0) ** k * math.pi / 4
+    hk = 2 * h * np.cos((2 * k + 1) * math.pi / (2 * n_band) * t + p)
+    return _center_pad_next_pow_2(hk)
+
+
+class PQMF(nn.Module):
+    """PQMF(channels, attenuation, n_band).forward: [B, channels, N] -> [B, channels * n_band, N / n_band]; every channel is
+    analysed on its own ('b c t -> (b c) 1 t', filterbank, '(b c) k t -> b (c k) t').  One aa_pqmf_analysis_f32 launch."""
+
+    def __init__(self, channels, attenuation, n_band):
+        super().__init__()
+        self.channels, self.attenuation, self.n_band = channels, attenuation, n_band
+        hk = torch.from_numpy(pqmf_filterbank(attenuation, n_band)).float() if n_band > 1 else torch.ones(1, 1)
+        self.register_buffer("hk", hk)
+
+    def forward(self, x):
+        if self.n_band == 1:
+            return x
+        x = _f32c(x, "waveform")
+        assert x.dim() == 3 and x.shape[1] == self.channels, f"expected [B,{self.channels},N], got {tuple(x.shape)}"
+        b, c, n = x.shape
+        taps = self.hk.shape[1]
+        t_out = (n + 2 * (taps // 2) - taps) // self.n_band
+        hk = self.hk.to(x.device)
+        out = torch.empty((b, c * self.n_band, t_out), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.aa_pqmf_analysis_f32(ptr(x), b * c, n, ptr(hk), self.n_band, taps, ptr(out), stream_ptr()))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Memcodes quantiser (restated `nwt_pytorch.Memcodes` / `dvae.residual_memcodes.ResidualMemcodes`; unpinned upstream)
+# ---------------------------------------------------------------------------------------------------
+
+class Memcodes(nn.Module):
+    """Multi-head codebook lookup: queries = head slices of the input (scaled by (dim/heads)^-0.5), keys / values = grouped 1x1
+    convolutions of the learned codes; eval mode picks argmax of the logits and returns that code's value.
+    forward takes the reference's [B, N, dim] layout; `quantize_cf` is the channel-major entry encode_it uses (no rearrange)."""
+
+    def __init__(self, *, dim, num_codes, heads=8, temperature=1.):
+        super().__init__()
+        assert dim % heads == 0, 'dimension must be divisible by number of heads'
+        self.heads, self.dim, self.num_codes, self.temperature = heads, dim, num_codes, temperature
+        self.scale = (dim // heads) ** -0.5
+        self.codes = nn.Parameter(torch.randn(heads, num_codes, dim // heads))
+        self.to_k = nn.Conv1d(dim, dim, 1, groups=heads, bias=False)
+        self.to_v = nn.Conv1d(dim, dim, 1, groups=heads, bias=False)
+
+    def get_codes(self):
+        "k, v [heads, num_codes, dim/heads]"
+        d = self.dim // self.heads
+        codes = _f32c(self.codes.detach(), "codes")
+        wk, wv = _f32c(self.to_k.weight.detach().reshape(self.dim, d)), _f32c(self.to_v.weight.detach().reshape(self.dim, d))
+        k, v = torch.empty_like(codes), torch.empty_like(codes)
+        with torch.cuda.device(codes.device):
+            check(lib.aa_memcodes_kv_f32(ptr(codes), ptr(wk), ptr(wv), self.heads, self.num_codes, d, ptr(k), ptr(v), stream_ptr()))
+        return k, v
+
+    def quantize_cf(self, x, resid_out=None, acc=None, final_tanh=False, want_indices=True):
+        "x [B, dim, N] channel-major -> (quantized [B, dim, N], indices [B, heads, N])"
+        if self.training:
+            raise NotImplementedError("Memcodes: the gumbel-softmax sampling path (training mode) is not built; call .eval()")
+        x = _f32c(x, "embeddings")
+        assert x.dim() == 3 and x.shape[1] == self.dim
+        b, _, n = x.shape
+        k, v = self.get_codes()
+        q = torch.empty_like(x)
+        idx = torch.empty((b, self.heads, n), dtype=torch.int64, device=x.device) if want_indices else None
+        with torch.cuda.device(x.device):
+            check(lib.aa_memcodes_quantize_f32(ptr(x), b, self.heads, self.dim // self.heads, n, ptr(k), ptr(v), self.num_codes,
+                                               float(self.scale), ptr(q), None if resid_out is None else ptr(resid_out),
+                                               None if acc is None else ptr(acc), int(final_tanh), None if idx is None else ptr(idx),
+                                               stream_ptr()))
+        return q, idx
+
+    def forward(self, x, *, merge_output_heads=True):
+        assert x.shape[-1] == self.dim
+        q, idx = self.quantize_cf(x.transpose(1, 2))
+        out = q.transpose(1, 2)
+        if not merge_output_heads:
+            out = out.reshape(out.shape[0], out.shape[1], self.heads, -1).permute(0, 2, 1, 3)
+        return out, idx
+
+
+class ResidualMemcodes(nn.Module):
+    "residual VQ over Memcodes layers: each layer quantises what the previous ones left; outputs are summed"
+
+    def __init__(self, *, num_quantizers, **kwargs):
+        super().__init__()
+        self.layers = nn.ModuleList([Memcodes(**kwargs) for _ in range(num_quantizers)])
+
+    def quantize_cf(self, x, final_tanh=False):
+        x = _f32c(x, "embeddings")
+        acc = torch.zeros_like(x)
+        residual, all_idx = x, []
+        for i, layer in enumerate(self.layers):
+            nxt = torch.empty_like(x)
+            _, idx = layer.quantize_cf(residual, resid_out=nxt, acc=acc, final_tanh=final_tanh and i == len(self.layers) - 1)
+            residual = nxt
+            all_idx.append(idx)
+        return acc, torch.stack(all_idx)
+
+    def forward(self, x):
+        q, idx = self.quantize_cf(x.transpose(1, 2))
+        return q.transpose(1, 2), idx
+
+
+def load_dvae_encoder_checkpoint(model, ckpt_path, map_location="cpu"):
+    """Loads the encoder / encoder_ema weights of the reference's Lightning checkpoint (given_models.py:340-356 does
+    `self.model.load_state_dict(ckpt['state_dict'])` on the whole DVAE) into the restated encoder.  The upstream encoder is an
+    nn.Sequential, so its keys look like `encoder.layers.<i>....{weight,bias}` (or weight_g / weight_v under weight_norm) in
+    layer order; they are mapped onto flat_convs() IN ORDER with strict count and shape checks -- any mismatch raises, which is
+    how a wrong guess at the upstream architecture would surface.  Real-checkpoint parity is UNTESTED:
+    the 4 GB checkpoint is not reachable from this build."""
+    ckpt = torch.load(ckpt_path, map_location=map_location, weights_only=False)
+    sd = ckpt.get("state_dict", ckpt)
+    loaded = {}
+    for prefix, target in (("encoder.", model.encoder), ("encoder_ema.", model.encoder_ema)):
+        keys = [k for k in sd if k.startswith(prefix)]
+        convs = []   # (weight, bias) in checkpoint order
+        names = sorted({k.rsplit(".", 1)[0] for k in keys}, key=lambda n: [int(t) if t.isdigit() else t for t in n.split(".")])
+        for nme in names:
+            if nme + ".weight_g" in sd and nme + ".weight_v" in sd:     # fold weight_norm: w = g * v / ||v|| (norm over all dims but 0)
+                g, v = sd[nme + ".weight_g"].float(), sd[nme + ".weight_v"].float()
+                w = v * (g / v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1))))
+            elif nme + ".weight" in sd:
+                w = sd[nme + ".weight"].float()
+            else:
+                continue
+            if w.dim() != 3:
+                continue
+            convs.append((nme, w, sd.get(nme + ".bias")))
+        mine = target.flat_convs()
+        if len(convs) != len(mine):
+            raise RuntimeError(f"{prefix}* holds {len(convs)} Conv1d layers, the restated encoder has {len(mine)}: the checkpoint's "
+                               "architecture differs from SURVEY.md Appendix A")
+        with torch.no_grad():
+            for conv, (nme, w, b) in zip(mine, convs):
+                if tuple(w.shape) != tuple(conv.weight.shape):
+                    raise RuntimeError(f"{nme}: weight {tuple(w.shape)} does not fit {tuple(conv.weight.shape)}")
+                if b is None or tuple(b.shape) != tuple(conv.bias.shape):
+                    raise RuntimeError(f"{nme}: bias missing or of the wrong shape")
+                conv.weight.copy_(w.to(conv.weight.device))
+                conv.bias.copy_(b.float().to(conv.bias.device))
+        loaded[prefix] = len(convs)
+    return loaded
+
+
 class DiffusionDVAE(nn.Module):
     """global_args needs: pqmf_bands, latent_dim, num_quantizers (ema_decay etc. are accepted and ignored).
     Same members as the reference on the encode side: encoder, encoder_ema (deepcopy), pqmf_bands, quantized."""
@@ -176,7 +374,7 @@ class DiffusionDVAE(nn.Module):
         super().__init__()
         self.pqmf_bands = global_args.pqmf_bands
         if self.pqmf_bands > 1:
-            raise NotImplementedError("pqmf_bands > 1 (PQMF analysis front-end) is a 'next' row, not built yet")
+            self.pqmf = PQMF(2, 70, global_args.pqmf_bands)
         capacity = 32
         c_mults = [2, 4, 8, 16, 32]
         strides = [4, 4, 2, 2, 2]
@@ -187,7 +385,13 @@ class DiffusionDVAE(nn.Module):
         self.num_quantizers = getattr(global_args, "num_quantizers", 0)
         self.quantized = self.num_quantizers > 0
         if self.quantized:
-            raise NotImplementedError("num_quantizers > 0 (Memcodes) is a 'next' row, not built yet")
+            quantizer_class = ResidualMemcodes if self.num_quantizers > 1 else Memcodes
+            quantizer_kwargs = {}
+            if self.num_quantizers > 1:
+                quantizer_kwargs["num_quantizers"] = self.num_quantizers
+            self.quantizer = quantizer_class(dim=global_args.latent_dim, heads=global_args.num_heads, num_codes=global_args.codebook_size,
+                                             temperature=1., **quantizer_kwargs)
+            self.quantizer_ema = deepcopy(self.quantizer)
         self.ema_decay = getattr(global_args, "ema_decay", 0.995)
         self.demo_reals_shape = None
 
@@ -214,11 +418,25 @@ class DiffusionDVAE(nn.Module):
         raise NotImplementedError("the diffusion decoder is outside the accelerated hot path (encode side only)")
 
     def encode_it(self, demo_reals):
-        "aa_mixer.py:175-195: tanh(encoder_ema(x)); runs under no_grad like the reference"
-        encoder_input = demo_reals.to(self.device)
+        """aa_mixer.py:175-195: (pqmf) -> encoder_ema -> (Memcodes) -> tanh; runs under no_grad like the reference.  Unbatched [C, N]
+        input is accepted like the reference's Conv1d stack accepts it."""
+        squeeze = demo_reals.dim() == 2
+        encoder_input = (demo_reals.unsqueeze(0) if squeeze else demo_reals).to(self.device)
         self.demo_reals_shape = demo_reals.shape
         with torch.no_grad():
-            return self.encoder_ema.encode_mix([encoder_input], None, apply_tanh=True)
+            if self.pqmf_bands > 1:
+                encoder_input = self.pqmf(encoder_input)
+            if not self.quantized:
+                emb = self.encoder_ema.encode_mix([encoder_input], None, apply_tanh=True)
+            else:
+                emb = self.encoder_ema.encode_mix([encoder_input], None, apply_tanh=False)
+                if isinstance(self.quantizer_ema, ResidualMemcodes):
+                    emb, _ = self.quantizer_ema.quantize_cf(emb, final_tanh=True)
+                else:
+                    acc = torch.zeros_like(emb)
+                    self.quantizer_ema.quantize_cf(emb, acc=acc, final_tanh=True, want_indices=False)
+                    emb = acc
+        return emb.squeeze(0) if squeeze else emb
 
     def decode_it(self, *args, **kwargs):
         raise NotImplementedError("the diffusion decoder is outside the accelerated hot path (encode side only)")

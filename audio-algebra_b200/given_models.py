@@ -347,7 +347,16 @@ class DVAEWrapper(GivenModelClass):
         """The reference downloads the 4 GB Lightning checkpoint here (given_models.py:340-356) and keeps
         random weights when that fails; there is no network in this build, so weights stay as initialised
         (or as loaded through load_state_dict / model.load_oracle_weights)."""
-        if self.debug:
+        path = os.path.expanduser(self.ckpt_info['ckpt_path'])
+        if os.path.exists(path):
+            from .DiffusionDVAE import load_dvae_encoder_checkpoint
+            try:   # same failure policy as the reference (:351-354): report and keep the current weights
+                n = load_dvae_encoder_checkpoint(self.model, path)
+                if self.debug:
+                    print(f"DVAEWrapper.setup: loaded encoder weights from {path}: {n}")
+            except Exception as e:
+                print(f"DVAEWrapper.setup: could not load {path} ({e}); going with current weights")
+        elif self.debug:
             print("DVAEWrapper.setup: no checkpoint download in this build; keeping current encoder weights")
 
     def encode_it(self, demo_reals):

@@ -156,6 +156,22 @@ int aa_batchnorm_fwd_f32(const float* x, int64_t n, int c, const float* gamma, c
 int aa_batchnorm_bwd_f32(const float* x, const float* gy, int64_t n, int c, const float* gamma, const float* save, int training,
                          float* gx, float* ggamma, float* gbeta, void* stream);
 
+/* --- dormant branches of DiffusionDVAE.encode_it (aa_mixer.py:178-179, 189-192; csrc/quant_pqmf.cu) ------------------------ */
+/* PQMF analysis (third-party diffusion.pqmf.PQMF(2, 70, bands).forward, classic form): x [rows][n] -> out [rows][bands][t_out],
+ * t_out = (n + 2*(taps/2) - taps) / bands; out[row][k][t] = sum_j hk[k][j] xpad[row][t*bands + j] with xpad zero-padded by taps/2,
+ * then the even samples of the odd bands are negated ("reverse_half").  hk [bands][taps] is designed on the host. */
+int aa_pqmf_analysis_f32(const float* x, int64_t rows, int64_t n, const float* hk, int bands, int taps, float* out, void* stream);
+/* Memcodes (third-party nwt_pytorch.Memcodes, eval path): keys / values of the codes, k[h][j][:] = Wk[h] codes[h][j][:] (grouped
+ * 1x1 Conv1d, wk [heads*d][d]) ... */
+int aa_memcodes_kv_f32(const float* codes, const float* wk, const float* wv, int heads, int n_codes, int d, float* k_out,
+                       float* v_out, void* stream);
+/* ... and the lookup: x [B][heads*d][N] (channel-major, what encoder_ema returns); per (b, head, n): j* = argmax_j <scale * x_slice,
+ * k[h][j]>, quantized = v[h][j*].  Any of q_out (quantized), resid_out (x - quantized), acc (+= quantized, tanh afterwards when
+ * final_tanh), idx_out ([B][heads][N] int64) may be NULL: one call per layer of dvae.residual_memcodes.ResidualMemcodes. */
+int aa_memcodes_quantize_f32(const float* x, int64_t batch, int heads, int d, int64_t n_pos, const float* k, const float* v,
+                             int n_codes, float scale, float* q_out, float* resid_out, float* acc, int final_tanh,
+                             int64_t* idx_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Losses (aa_mixer.py:344-364; L2-hinge variant train_aa_effects.py:42-46).
  * z is [B][D] f32 (D = C*T flattened features), the batch dimension is the statistics dimension.

@@ -287,3 +287,125 @@ def test_other_encoder_configs_on_the_tensor_core_paths(setup, in_ch, c_mults, s
         else:
             cos = torch.nn.functional.cosine_similarity(y.flatten(1).double().cpu(), yr.flatten(1).double(), dim=1)
             assert cos.min().item() >= 0.999, (mode, cos)
+
+
+# ---- dormant branches of encode_it (aa_mixer.py:178-179, 189-192): PQMF front-end, Memcodes quantiser ------------------------------
+class _Args:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+@pytest.mark.parametrize("bands,n", [(2, 4096), (4, 8192), (8, 8192), (4, 5000)])
+def test_pqmf_analysis_kernel(bands, n):
+    "aa_pqmf_analysis_f32 against the oracle's conv1d restatement, the same filterbank on both sides; the bank is designed twice"
+    import audio_algebra_b200 as aab
+    from audio_algebra_b200.DiffusionDVAE import PQMF
+    from oracle import aa_oracle as O
+    pq = PQMF(2, 70, bands).cuda()
+    hk_o = O.pqmf_filterbank(70, bands)
+    assert rel_l2(pq.hk, hk_o) < 1e-6                      # product-side and oracle-side designs agree
+    x = _x((3, 2, n), bands)
+    y = pq(x.cuda())
+    ref = O.pqmf_analysis(x.double(), hk_o)
+    assert tuple(y.shape) == tuple(ref.shape) == (3, 2 * bands, n // bands)
+    assert rel_l2(y, ref) < 1e-5
+
+
+def test_encode_it_with_pqmf_front_end():
+    "pqmf_bands = 4: [B, 2, N] -> PQMF -> encoder with 8 input channels (generic fp32 conv kernel) -> tanh"
+    import audio_algebra_b200 as aab
+    from oracle import aa_oracle as O
+    torch.manual_seed(3)
+    enc_o = O.SoundStreamXLEncoderOracle(in_channels=8).eval()
+    m = aab.DiffusionDVAE(_Args(pqmf_bands=4, latent_dim=64, num_quantizers=0)).eval()
+    m.load_oracle_weights(enc_o)
+    m = m.cuda()
+    x = _x((2, 2, 16384), 5)
+    y = m.encode_it(x.cuda())
+    ref = torch.tanh(enc_o(O.pqmf_analysis(x, O.pqmf_filterbank(70, 4).float())))
+    assert tuple(y.shape) == tuple(ref.shape) == (2, 64, 16384 // 4 // 128)
+    assert rel_l2(y, ref) < 1e-3
+
+
+@pytest.mark.parametrize("heads,codes_n,nq", [(8, 1024, 1), (4, 64, 1), (8, 256, 3)])
+def test_memcodes_quantiser(heads, codes_n, nq):
+    "Memcodes / ResidualMemcodes lookup (eval path) against the oracle restatement: same indices, same values"
+    from audio_algebra_b200.DiffusionDVAE import Memcodes, ResidualMemcodes
+    from oracle import aa_oracle as O
+    torch.manual_seed(heads + nq)
+    q = (ResidualMemcodes(num_quantizers=nq, dim=64, heads=heads, num_codes=codes_n) if nq > 1 else Memcodes(dim=64, heads=heads, num_codes=codes_n))
+    q = q.cuda().eval()
+    x = torch.randn(3, 64, 70, generator=torch.Generator().manual_seed(1))
+    layers = list(q.layers) if nq > 1 else [q]
+    params = [(l.codes.detach().cpu().double(), l.to_k.weight.detach().cpu().double().reshape(64, -1), l.to_v.weight.detach().cpu().double().reshape(64, -1))
+              for l in layers]
+    out, idx = q.quantize_cf(x.cuda())
+    if nq > 1:
+        ref, ridx = O.residual_memcodes_eval(x.double(), params, heads)
+        same = (idx.cpu() == ridx).float().mean().item()
+    else:
+        ref, ridx = O.memcodes_eval(x.double(), *params[0], heads)
+        same = (idx.cpu() == ridx).float().mean().item()
+    assert same > 0.995                                    # fp32 vs fp64 logits may flip a near tie
+    if same == 1.0:
+        assert rel_l2(out, ref) < 1e-5
+    # reference layout: [B, N, dim] in, ([B, N, dim], indices) out
+    o2, i2 = q(x.cuda().transpose(1, 2))
+    assert tuple(o2.shape) == (3, 70, 64) and torch.equal(o2.transpose(1, 2), out)
+    with pytest.raises(NotImplementedError):
+        q.train()(x.cuda().transpose(1, 2))
+
+
+def test_encode_it_quantised_branch():
+    "num_quantizers = 1 / 2: tanh(quantizer_ema(encoder_ema(x))), rearranges folded into index math"
+    import audio_algebra_b200 as aab
+    from oracle import aa_oracle as O
+    for nq in (1, 2):
+        torch.manual_seed(11)
+        enc_o = O.SoundStreamXLEncoderOracle().eval()
+        m = aab.DiffusionDVAE(_Args(pqmf_bands=1, latent_dim=64, num_quantizers=nq, num_heads=8, codebook_size=128)).eval()
+        m.load_oracle_weights(enc_o)
+        m = m.cuda()
+        x = _x((2, 2, 8192), 6)
+        y = m.encode_it(x.cuda())
+        emb = m.encoder_ema(x.cuda())                      # quantise the SAME fp32 embeddings on both sides (argmax is discontinuous)
+        layers = list(m.quantizer_ema.layers) if nq > 1 else [m.quantizer_ema]
+        params = [(l.codes.detach().cpu().double(), l.to_k.weight.detach().cpu().double().reshape(64, -1),
+                   l.to_v.weight.detach().cpu().double().reshape(64, -1)) for l in layers]
+        ref = (O.residual_memcodes_eval(emb.cpu().double(), params, 8) if nq > 1 else O.memcodes_eval(emb.cpu().double(), *params[0], 8))[0]
+        assert tuple(y.shape) == (2, 64, 64)
+        bad = ((y.cpu().double() - torch.tanh(ref)).abs() > 1e-4).float().mean().item()
+        assert bad < 0.01                                  # a flipped near-tie changes 8 of 64 channels at one position
+        assert y.abs().max() <= 1.0
+    assert m.encode_it(x[0].cuda()).shape == (64, 64)      # unbatched [C, N] input, like the reference's Conv1d stack accepts
+
+
+def test_dvae_checkpoint_loader(tmp_path):
+    "Lightning-style state_dict (encoder.layers.*, encoder_ema.layers.*; plain and weight-normed convs) -> flat_convs() in order"
+    import audio_algebra_b200 as aab
+    from audio_algebra_b200.DiffusionDVAE import load_dvae_encoder_checkpoint
+    from oracle import aa_oracle as O
+    torch.manual_seed(4)
+    enc_o = O.SoundStreamXLEncoderOracle().eval()
+    sd = {}
+    for i, (w, b) in enumerate(enc_o.flat_weights()):
+        for pre in ("encoder", "encoder_ema"):
+            if i % 2 == 0:
+                sd[f"{pre}.layers.{i}.weight"], sd[f"{pre}.layers.{i}.bias"] = w.detach().clone(), b.detach().clone()
+            else:                                          # weight_norm parametrisation of the same weight
+                g = w.detach().flatten(1).norm(dim=1).view(-1, 1, 1)
+                sd[f"{pre}.layers.{i}.weight_g"], sd[f"{pre}.layers.{i}.weight_v"] = g, w.detach() * 3.0
+                sd[f"{pre}.layers.{i}.bias"] = b.detach().clone()
+    sd["diffusion.net.0.weight"] = torch.zeros(4, 4, 3)   # other members of the DVAE are ignored
+    path = tmp_path / "dvae.ckpt"
+    torch.save({"state_dict": sd}, path)
+    dv = aab.DVAEWrapper(debug=False)
+    n_l = len(enc_o.flat_weights())
+    assert load_dvae_encoder_checkpoint(dv.model, str(path)) == {"encoder.": n_l, "encoder_ema.": n_l}
+    dv = dv.cuda()
+    x = _x((1, 2, 4096), 8)
+    assert rel_l2(dv.encode(x.cuda()), O.dvae_encode_it(enc_o, x)) < 1e-3
+    del sd["encoder.layers.5.bias"]
+    torch.save({"state_dict": sd}, path)
+    with pytest.raises(RuntimeError):
+        load_dvae_encoder_checkpoint(aab.DVAEWrapper(debug=False).model, str(path))
