@@ -8,8 +8,8 @@ __version__ = "0.1.0"
 
 from . import _lib  # noqa: F401  (loads libaa_b200.so or raises)
 from .given_models import (GivenModelClass, SpectrogramAE, MagSpectrogramAE, MagDPhaseSpectrogramAE,  # noqa: F401
-                           MelSpectrogramAE, DVAEWrapper, encode_all)
+                           MelSpectrogramAE, DVAEWrapper, StackedDiffAEWrapper, encode_all)
 from .aa_mixer import (EmbedBlock, AudioAlgebra, get_stems_faders, do_mixing, mseloss, vicreg_var_loss,  # noqa: F401
                        vicreg_var_loss_l2, vicreg_cov_loss, off_diagonal, latent_lincomb)
 from .DiffusionDVAE import DiffusionDVAE, SoundStreamXLEncoder  # noqa: F401
-from . import aa_mixer, aa_effects, latent_ops, pca, given_models, parallel, training  # noqa: F401
+from . import aa_mixer, aa_effects, latent_ops, pca, given_models, parallel, training, StackedAELatentDiffusionCond  # noqa: F401

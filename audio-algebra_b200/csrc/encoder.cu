@@ -215,6 +215,30 @@ static bool fp32_on_tensor_cores(const AaEncoder* e) {
   return e->tf_ok && getenv("AA_ENC_FP32_CUDA_CORES") == nullptr;
 }
 
+// Generic fp32 Conv1d on channel-major tensors (the same CUDA-core kernel the fp32 encoder path uses), exported for the given
+// models whose layers are not in the SoundStreamXL table (StackedDiffAE's Encoder1d: 1x1 / k3 / strided k5 convs).
+// out = act(conv(x) + bias (+ res)); act: 0 none, 1 ELU, 2 tanh.  x [B][cin][lin], w [cout][cin][k], res / out [B][cout][lout].
+int aa_conv1d_f32(const float* x, int64_t batch, int cin, int64_t lin, const float* w, const float* bias, int cout, int k, int stride,
+                  int dil, int pad, const float* res, int act, float* out, void* stream) {
+  AA_REQUIRE(x && w && bias && out, "NULL tensor");
+  AA_REQUIRE(batch >= 0 && batch <= 65535 && cin >= 1 && cout >= 1 && lin >= 1 && lin < (1LL << 31), "bad shape");
+  AA_REQUIRE(k >= 1 && k <= 8 && stride >= 1 && dil >= 1 && pad >= 0, "bad conv geometry");
+  AA_REQUIRE((LT - 1) * stride + (k - 1) * dil + 1 <= XW, "stride %d / kernel %d / dilation %d: input strip too wide for the kernel", stride, k, dil);
+  AA_REQUIRE(act >= 0 && act <= 2, "act=%d", act);
+  if (batch == 0) return AA_OK;
+  const int64_t lout = (lin + 2 * pad - (int64_t)dil * (k - 1) - 1) / stride + 1;
+  AA_REQUIRE(lout >= 1, "input too short");
+  ConvArgs a{};
+  a.n_in = 1; a.x[0] = x; a.fader[0] = 1.0f;
+  a.w = w; a.bias = bias; a.res = res; a.out = out;
+  a.cin = cin; a.cout = cout; a.lin = (int)lin; a.lout = (int)lout; a.k = k; a.stride = stride; a.dil = dil; a.pad = pad;
+  a.elu = act == 1; a.tanh_out = act == 2;
+  dim3 grid((unsigned)((lout + LT - 1) / LT), (unsigned)((cout + CT - 1) / CT), (unsigned)batch);
+  conv1d_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  AA_LAUNCH_CHECK();
+  return AA_OK;
+}
+
 int aa_encoder_out_length(const AaEncoder* e, int64_t n, int64_t* t_out) {
   AA_REQUIRE(e && t_out, "NULL argument");
   int64_t l = n;

@@ -270,6 +270,45 @@ __global__ void bn_bwd_kernel(const float* __restrict__ x, const float* __restri
   }
 }
 
+// ---- GroupNorm (+ SiLU) over channel-major [B][C][L]: the C/G channels of a group are one contiguous run of (C/G)*L floats ----
+// one block per (batch, group): mean, then centred second moment (two passes over data that sits in L2), then normalise,
+// per-channel affine and x * sigmoid(x)
+__global__ void __launch_bounds__(kThreads) groupnorm_act_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, int c, long long l, int groups, float eps,
+                                                                 int silu, float* __restrict__ out) {
+  __shared__ float sh[kThreads];
+  __shared__ float s_mean, s_rstd;
+  const int g = blockIdx.x % groups;
+  const long long b = blockIdx.x / groups;
+  const int cpg = c / groups;
+  const long long n = (long long)cpg * l;
+  const float* xg = x + (b * c + (long long)g * cpg) * l;
+  float* og = out + (b * c + (long long)g * cpg) * l;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += kThreads) acc += xg[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s_ = kThreads / 2; s_ > 0; s_ >>= 1) { if ((int)threadIdx.x < s_) sh[threadIdx.x] += sh[threadIdx.x + s_]; __syncthreads(); }
+  if (threadIdx.x == 0) s_mean = sh[0] / (float)n;
+  __syncthreads();
+  const float mean = s_mean;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < n; i += kThreads) { const float d = xg[i] - mean; q = fmaf(d, d, q); }
+  __syncthreads();
+  sh[threadIdx.x] = q;
+  __syncthreads();
+  for (int s_ = kThreads / 2; s_ > 0; s_ >>= 1) { if ((int)threadIdx.x < s_) sh[threadIdx.x] += sh[threadIdx.x + s_]; __syncthreads(); }
+  if (threadIdx.x == 0) s_rstd = rsqrtf(sh[0] / (float)n + eps);
+  __syncthreads();
+  const float rstd = s_rstd;
+  for (long long i = threadIdx.x; i < n; i += kThreads) {
+    const int ch = g * cpg + (int)(i / l);
+    float v = (xg[i] - mean) * rstd * (gamma ? gamma[ch] : 1.f) + (beta ? beta[ch] : 0.f);
+    if (silu) v = v / (1.0f + expf(-v));
+    og[i] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -413,6 +452,17 @@ int aa_batchnorm_bwd_f32(const float* x, const float* gy, int64_t n, int c, cons
   AA_REQUIRE(x && gy && save, "NULL tensor");
   AA_REQUIRE(n >= 1 && c >= 1, "bad shape");
   bn_bwd_kernel<<<(unsigned)c, kThreads, 0, (cudaStream_t)stream>>>(x, gy, n, c, gamma, save, training, gx, ggamma, gbeta);
+  AA_LAUNCH_CHECK();
+  return AA_OK;
+}
+
+int aa_groupnorm_act_f32(const float* x, int64_t batch, int c, int64_t l, const float* gamma, const float* beta, int groups, float eps, int silu,
+                         float* out, void* stream) {
+  AA_REQUIRE(x && out, "NULL tensor");
+  AA_REQUIRE(batch >= 0 && c >= 1 && l >= 1 && groups >= 1 && c % groups == 0, "channels %d not divisible by %d groups", c, groups);
+  AA_REQUIRE(batch * groups < (1LL << 31), "too many (batch, group) pairs");
+  if (batch == 0) return AA_OK;
+  groupnorm_act_kernel<<<(unsigned)(batch * groups), kThreads, 0, (cudaStream_t)stream>>>(x, gamma, beta, c, l, groups, eps, silu, out);
   AA_LAUNCH_CHECK();
   return AA_OK;
 }

@@ -16,7 +16,8 @@ import torch.nn as nn
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 
-__all__ = ['encode_all', 'GivenModelClass', 'SpectrogramAE', 'MagSpectrogramAE', 'MagDPhaseSpectrogramAE', 'MelSpectrogramAE', 'DVAEWrapper']
+__all__ = ['encode_all', 'GivenModelClass', 'SpectrogramAE', 'MagSpectrogramAE', 'MagDPhaseSpectrogramAE', 'MelSpectrogramAE', 'DVAEWrapper',
+           'StackedDiffAEWrapper']
 
 
 class GivenModelClass(nn.Module):
@@ -370,22 +371,90 @@ class DVAEWrapper(GivenModelClass):
         return reps.cpu() if on_cpu else reps
 
 
-def encode_all(given_model, data, batch_size=64, out=None, device=None):
+class StackedDiffAEWrapper(GivenModelClass):
+    """Wrapper for the stacked latent diffusion autoencoder (given_models.py:361-417): encode(reals) returns the coarsest single
+    stage of representations, tanh(latent_encoder(autoencoder.encode(reals))): [B, 2, N] -> [B, 32, N / 512].  Constructor
+    arguments, members (first_stage_config, first_stage_autoencoder, model, latent_dim, latent_downsampling_ratio, ckpt_info) and
+    the post-setup aliasing (latent_encoder = latent_encoder_ema) follow the reference; the decoders raise."""
+
+    def __init__(self, debug=True, first_stage_config=None, ckpt_info=None, **kwargs):
+        super().__init__()
+        from .StackedAELatentDiffusionCond import AudioAutoencoder, LatentAudioDiffusionAutoencoder
+        self.debug = debug
+        self.first_stage_config = first_stage_config if first_stage_config is not None else \
+            {"capacity": 64, "c_mults": [2, 4, 8, 16, 32], "strides": [2, 2, 2, 2, 2], "latent_dim": 32}
+        cfg = dict(self.first_stage_config, **{k: v for k, v in kwargs.items() if k == "compute_dtype"})
+        self.first_stage_autoencoder = AudioAutoencoder(**cfg).requires_grad_(False)
+        self.model = LatentAudioDiffusionAutoencoder(autoencoder=self.first_stage_autoencoder)
+        self.latent_dim = self.model.latent_dim
+        self.latent_downsampling_ratio = self.model.latent_downsampling_ratio
+        self.ckpt_info = ckpt_info if ckpt_info is not None else \
+            {'ckpt_path': '~/checkpoints/stacked-diffae-more-310k.ckpt',
+             'ckpt_hash': '91f33839ecb6e3c41b1e89e1a9e0de0dac2ebe1795efa034797429c202600a58',
+             'ckpt_url': '', 'gdrive_path': ''}
+
+    def encode(self, reals: torch.Tensor) -> torch.Tensor:
+        self.orig_shape = reals.shape
+        on_cpu = not reals.is_cuda
+        dev = next(self.model.parameters()).device
+        reps = self.model.encode(reals.to(dev))
+        return reps.cpu() if on_cpu else reps
+
+    def setup(self, gdrive=True):
+        """The reference loads `stacked-diffae-more-310k.ckpt` with LatentAudioDiffusionAutoencoder.load_from_checkpoint (keeping random
+        weights when that fails, :397-402) and then makes the EMA copies the live ones (:404-407).  No checkpoint is reachable from
+        this build; the aliasing is reproduced."""
+        if self.debug:
+            print(f"{self.__class__.__name__}: no checkpoint download in this build; going with current weights")
+        if hasattr(self.model, "latent_encoder_ema"):
+            self.model.latent_encoder = self.model.latent_encoder_ema
+            del self.model.latent_encoder_ema
+        self.model.eval()
+
+
+def _npy_shards(save_path, n, tail_shape, dtype, shard_rows):
+    "file-backed output: one .npy (np.lib.format.open_memmap) or `stem_00000.npy`, ... of shard_rows rows each; returns [(lo, hi, memmap)]"
+    import numpy as np
+    if not shard_rows or shard_rows >= n:
+        return [(0, n, np.lib.format.open_memmap(save_path, mode="w+", dtype=dtype, shape=(n,) + tail_shape))], [save_path]
+    stem = save_path[:-4] if save_path.endswith(".npy") else save_path
+    shards, names = [], []
+    for k, lo in enumerate(range(0, n, shard_rows)):
+        hi = min(lo + shard_rows, n)
+        names.append(f"{stem}_{k:05d}.npy")
+        shards.append((lo, hi, np.lib.format.open_memmap(names[-1], mode="w+", dtype=dtype, shape=(hi - lo,) + tail_shape)))
+    return shards, names
+
+
+def encode_all(given_model, data, batch_size=64, out=None, device=None, save_path=None, shard_rows=None):
     """Bulk encode loop of the reference (xae_dataset.ipynb cell 50 `encode_all`, effects_explorer.ipynb cell 36):
 
-        reps[i:i+bs] = given_model.encode(data[i:i+bs].to(device)).cpu()
+        reps[i:i+bs] = given_model.encode(data[i:i+bs].to(device)).cpu()     ...     np.save(reps_filename, reps_full)
 
-    with the three stages overlapped instead of run back to back: batch i+1 is copied host->device (from pinned
+    with the stages overlapped instead of run back to back: batch i+1 is copied host->device (from pinned
     staging, on a copy stream) while batch i is encoded, and the representations of batch i-1 return to the host
     on a third stream.  Encodes stay on ONE stream (a model's kernels share one workspace).  `data`: CPU tensor
     [Ntot, C, N]; `out`: optional preallocated CPU tensor [Ntot, ...] (pinned memory makes the return copy
-    asynchronous); returns it."""
+    asynchronous); returns it.  The notebook's positional order (audio_full, batch_size, given_model, device) is accepted too.
+    `save_path`: write the representations as .npy WHILE encoding (the notebook's np.save afterwards, without the second pass
+    over the data): batches land in pinned staging and a writer thread moves them into np.lib.format.open_memmap files --
+    one file, or `stem_00000.npy`, ... of `shard_rows` rows each; returns the list of files (np.load / np.load(mmap_mode='r'))."""
+    if torch.is_tensor(given_model) or type(given_model).__module__ == "numpy":
+        # the notebook's positional order: encode_all(audio_full, batch_size, given_model, device)
+        audio_full, bsz, gm, dv = given_model, data, batch_size, out
+        if not isinstance(gm, nn.Module) or not isinstance(bsz, int):
+            raise TypeError("expected encode_all(given_model, data, ...) or the notebook's encode_all(audio_full, batch_size, given_model, device)")
+        given_model, data, batch_size, out = gm, audio_full, bsz, None
+        device = dv if device is None else device
+    if not torch.is_tensor(data):
+        data = torch.from_numpy(data).float()
     if data.is_cuda:
         raise ValueError("encode_all takes the host-resident dataset tensor; call given_model.encode for device tensors")
     dev = torch.device(device) if device is not None else next((p.device for p in given_model.parameters() if p.is_cuda),
                                                                torch.device("cuda", torch.cuda.current_device()))
     n = data.shape[0]
     data = data.float() if data.dtype != torch.float32 else data
+    writer, shards, names, stage_out, wq = None, None, None, None, None
     with torch.cuda.device(dev):
         compute = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -415,16 +484,62 @@ def encode_all(given_model, data, batch_size=64, out=None, device=None):
                 reps = given_model.encode(d_in[s][:nb])
             ev_free[s].record(compute)
             used[s] = True
-            if out is None:
-                out = torch.empty((n,) + tuple(reps.shape[1:]), dtype=reps.dtype, pin_memory=True)
             ev_done = torch.cuda.Event()
             ev_done.record(compute)
+            if save_path is not None:
+                if writer is None:    # first batch fixes the representation shape: open the files, start the writer
+                    import queue
+                    import threading
+                    shards, names = _npy_shards(save_path, n, tuple(reps.shape[1:]), "float32" if reps.dtype == torch.float32 else str(reps.dtype).split(".")[-1],
+                                                shard_rows)
+                    stage_out = [torch.empty((bs,) + tuple(reps.shape[1:]), dtype=reps.dtype, pin_memory=True) for _ in range(3)]
+                    free_slots, wq = queue.Queue(), queue.Queue()
+                    for k in range(3):
+                        free_slots.put(k)
+
+                    def _write():
+                        while True:
+                            item = wq.get()
+                            if item is None:
+                                return
+                            slot, a, b_, ev = item
+                            ev.synchronize()
+                            arr = stage_out[slot][:b_ - a].numpy()
+                            for slo, shi, mm in shards:      # a batch may straddle shard boundaries
+                                c0, c1 = max(a, slo), min(b_, shi)
+                                if c0 < c1:
+                                    mm[c0 - slo:c1 - slo] = arr[c0 - a:c1 - a]
+                            free_slots.put(slot)
+
+                    writer = threading.Thread(target=_write, daemon=True)
+                    writer.start()
+                slot = free_slots.get()
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done)
+                    stage_out[slot][:nb].copy_(reps, non_blocking=True)
+                    ev_copied = torch.cuda.Event()
+                    ev_copied.record(s_out)
+                reps.record_stream(s_out)
+                wq.put((slot, lo, hi, ev_copied))
+                continue
+            if out is None:
+                out = torch.empty((n,) + tuple(reps.shape[1:]), dtype=reps.dtype, pin_memory=True)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done)
                 out[lo:hi].copy_(reps, non_blocking=True)
             reps.record_stream(s_out)
         s_out.synchronize()
         compute.synchronize()
+    if save_path is not None:
+        if writer is not None:
+            wq.put(None)
+            writer.join()
+            for _, _, mm in shards:
+                mm.flush()
+            return names
+        import numpy as np   # empty dataset
+        np.save(save_path, given_model.encode(data.to(dev)).cpu().numpy())
+        return [save_path]
     if out is None:   # empty dataset
         out = given_model.encode(data.to(dev)).cpu()
     return out

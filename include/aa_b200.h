@@ -172,6 +172,15 @@ int aa_memcodes_quantize_f32(const float* x, int64_t batch, int heads, int d, in
                              int n_codes, float scale, float* q_out, float* resid_out, float* acc, int final_tanh,
                              int64_t* idx_out, void* stream);
 
+/* --- generic layers for given models outside the SoundStreamXL layer table (StackedDiffAEWrapper, given_models.py:361-385) --------- */
+/* out = act(conv1d(x) + bias (+ res)), channel-major fp32: x [B][cin][lin], w [cout][cin][k], res / out [B][cout][lout];
+ * act: 0 none, 1 ELU, 2 tanh; k <= 8 */
+int aa_conv1d_f32(const float* x, int64_t batch, int cin, int64_t lin, const float* w, const float* bias, int cout, int k, int stride,
+                  int dil, int pad, const float* res, int act, float* out, void* stream);
+/* nn.GroupNorm(groups, c) (+ SiLU when silu != 0) on [B][c][l]; gamma / beta [c] or NULL */
+int aa_groupnorm_act_f32(const float* x, int64_t batch, int c, int64_t l, const float* gamma, const float* beta, int groups, float eps,
+                         int silu, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Losses (aa_mixer.py:344-364; L2-hinge variant train_aa_effects.py:42-46).
  * z is [B][D] f32 (D = C*T flattened features), the batch dimension is the statistics dimension.

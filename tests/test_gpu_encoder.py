@@ -289,6 +289,22 @@ def test_other_encoder_configs_on_the_tensor_core_paths(setup, in_ch, c_mults, s
             assert cos.min().item() >= 0.999, (mode, cos)
 
 
+def test_encode_all_notebook_signature_and_npy_writer(setup, tmp_path):
+    "xae_dataset.ipynb cell 50: encode_all(audio_full, batch_size, given_model, device) + np.save -- here written while encoding, optionally sharded"
+    import numpy as np
+    aab, O, enc_o, dv = setup
+    data = _x((11, 2, 4096), 21)
+    ref = aab.encode_all(dv, data, batch_size=4)
+    assert torch.equal(aab.encode_all(data, 4, dv, torch.device("cuda")), ref)          # the notebook's positional order
+    assert torch.equal(aab.encode_all(data.numpy(), 4, dv, "cuda"), ref)                 # ... which also takes the numpy array it loads
+    one = aab.encode_all(dv, data, batch_size=4, save_path=str(tmp_path / "reps.npy"))
+    assert one == [str(tmp_path / "reps.npy")] and np.array_equal(np.load(one[0]), ref.numpy())
+    many = aab.encode_all(dv, data, batch_size=4, save_path=str(tmp_path / "sh.npy"), shard_rows=5)   # batches straddle shard boundaries
+    assert [p.split("/")[-1] for p in many] == ["sh_00000.npy", "sh_00001.npy", "sh_00002.npy"]
+    assert np.array_equal(np.concatenate([np.load(p) for p in many]), ref.numpy())
+    assert [np.load(p, mmap_mode="r").shape[0] for p in many] == [5, 5, 1]
+
+
 # ---- dormant branches of encode_it (aa_mixer.py:178-179, 189-192): PQMF front-end, Memcodes quantiser ------------------------------
 class _Args:
     def __init__(self, **kw):
