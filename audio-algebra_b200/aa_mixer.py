@@ -421,26 +421,64 @@ def get_stems_faders(batch, dl_iter, dl, maxstems=2, unity_gain=False, debug=Fal
     return stems, faders.to(device), dl_iter
 
 
+class _LazyArchive(dict):
+    """The archive dict of do_mixing with its two waveform-sized entries ('fadedstems', 'mix') materialised on first access: the
+    training step never reads them (train_aa_mixer_accel.py:504-517 uses ymix / ymix_recon / yrecons), the demo code does."""
+
+    def __init__(self, eager, lazy):
+        super().__init__(eager)
+        self._lazy = dict(lazy)
+
+    def __getitem__(self, k):
+        if not dict.__contains__(self, k) and k in self._lazy:
+            dict.__setitem__(self, k, self._lazy.pop(k)())
+        return dict.__getitem__(self, k)
+
+    def __contains__(self, k):
+        return dict.__contains__(self, k) or k in self._lazy
+
+    def keys(self):
+        return list(dict.keys(self)) + list(self._lazy.keys())
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+
 def do_mixing(stems, faders, given_model, aa_model, device, debug=False, **kwargs):
     """aa_mixer.py:295-327.  Same outputs (zsum, zmix, archive).  The reference re-encodes the running
     mix after every stem and keeps only the last result; here the mix is encoded once after the loop
-    (identical zmix / archive['ymix'])."""
-    zs, ys, fadedstems, yrecons = [], [], [], []
+    (identical zmix / archive['ymix']).  Given models that expose `encode_mix` (the conv encoder) take the fader scaling and the
+    stem sum inside their first layer's load, so `fadedstem` / `mix` are not written to HBM unless the archive entry is read."""
+    zs, ys, yrecons = [], [], []
     fl = [float(f) for f in (faders.detach().cpu().tolist() if torch.is_tensor(faders) else faders)]
     stems = [s.to(device) for s in stems]
+    fused = hasattr(given_model, "encode_mix") and len(stems) <= 4
+    fadedstems = None if fused else []
     for s, f in zip(stems, fl):
-        fadedstem = latent_lincomb([s], [f])
         with torch.no_grad():
-            y = given_model.encode(fadedstem)
+            if fused:
+                y = given_model.encode_mix([s], [f])
+            else:
+                fadedstem = latent_lincomb([s], [f])
+                fadedstems.append(fadedstem)
+                y = given_model.encode(fadedstem)
         z, y_recon = aa_model(y)
-        yrecons.append(y_recon); zs.append(z); ys.append(y); fadedstems.append(fadedstem)
+        yrecons.append(y_recon); zs.append(z); ys.append(y)
     n = len(zs)
     zsum = _lincomb_ad(zs, [1.0] * n) if n > 1 else zs[0]
-    mix = latent_lincomb(stems[:n], fl[:n])
     with torch.no_grad():
-        ymix = given_model.encode(mix)
+        if fused:
+            mix = None
+            ymix = given_model.encode_mix(stems[:n], fl[:n])
+        else:
+            mix = latent_lincomb(stems[:n], fl[:n])
+            ymix = given_model.encode(mix)
         ysum = latent_lincomb(ys, [1.0] * n) if n > 1 else ys[0]
     zmix, ymix_recon = aa_model(ymix)
-    archive = {'zs': zs, 'mix': mix, 'ys': ys, 'ymix': ymix, 'ymix_recon': ymix_recon, 'fadedstems': fadedstems,
-               'yrecons': yrecons, 'ysum': ysum}
+    eager = {'zs': zs, 'ys': ys, 'ymix': ymix, 'ymix_recon': ymix_recon, 'yrecons': yrecons, 'ysum': ysum}
+    if fused:
+        archive = _LazyArchive(eager, {'mix': lambda: latent_lincomb(stems[:n], fl[:n]),
+                                       'fadedstems': lambda: [latent_lincomb([s], [f]) for s, f in zip(stems, fl)]})
+    else:
+        archive = dict(eager, mix=mix, fadedstems=fadedstems)
     return zsum, zmix, archive

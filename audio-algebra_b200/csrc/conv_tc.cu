@@ -28,7 +28,7 @@
 namespace {
 
 constexpr int BM = 128;             // output positions per tile (UMMA M)
-constexpr int kMaxChunks = 64;      // K chunks per tile
+constexpr int kMaxChunks = 128;     // K chunks per tile (C = 1024 with 7 taps: 112)
 constexpr int kMaxEpi = 4;          // epilogue warp groups (4 warps each); warp 0: TMA, warp 1: MMA
 constexpr int kTcMaxThreads = 64 + 128 * kMaxEpi;
 constexpr int kMaxAcc = 8;
@@ -437,6 +437,57 @@ __global__ void __launch_bounds__(256) conv_l0_kernel(const L0Args a) {
   }
 }
 
+// The same for wider first layers (cout <= 64, e.g. the capacity-64 first stage of StackedDiffAEWrapper): 128 positions per block.
+__global__ void __launch_bounds__(128) conv_l0_wide_kernel(const L0Args a) {
+  __shared__ float Xs[4][128 + 8];
+  __shared__ float Ws[64 * 4 * 7];
+  __shared__ float Bs[64];
+  __shared__ __align__(16) unsigned char Os[128 * (64 * 2 + 16)];
+  const int b = blockIdx.y, l0 = blockIdx.x * 128;
+  for (int e = threadIdx.x; e < a.cout * a.cin * a.k; e += 128) Ws[e] = a.w[e];
+  if (threadIdx.x < a.cout) Bs[threadIdx.x] = a.bias[threadIdx.x];
+  const int span = 128 + a.k - 1;
+  for (int e = threadIdx.x; e < a.cin * span; e += 128) {
+    const int c = e / span, j = e % span, pos = l0 - a.pad + j;
+    float v = 0.f;
+    if (pos >= 0 && pos < a.n) {
+      const long long off = ((long long)b * a.cin + c) * a.n + pos;
+      v = a.fader[0] * a.x[0][off];
+      for (int s = 1; s < a.n_in; ++s) v = fmaf(a.fader[s], a.x[s][off], v);
+    }
+    Xs[c][j] = v;
+  }
+  __syncthreads();
+  const int l = l0 + threadIdx.x;
+  const int RS = a.cout * 2 + 16;
+  for (int co0 = 0; co0 < a.cout; co0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = Bs[co0 + i];
+    for (int c = 0; c < a.cin; ++c)
+      for (int kk = 0; kk < a.k; ++kk) {
+        const float xv = Xs[c][threadIdx.x + kk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(Ws[((co0 + i) * a.cin + c) * a.k + kk], xv, acc[i]);
+      }
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float x0 = (l < a.n) ? elu1(acc[2 * i]) : 0.f, x1 = (l < a.n) ? elu1(acc[2 * i + 1]) : 0.f;
+      __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
+      w[i] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    *reinterpret_cast<uint4*>(Os + threadIdx.x * RS + co0 * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+  const int vpr = a.cout / 8;
+  uint4* o = reinterpret_cast<uint4*>(a.out + ((long long)b * a.row_stride + l0) * a.cout);
+  for (int idx = threadIdx.x; idx < 128 * vpr; idx += 128) {
+    const int rr = idx / vpr, cv = idx - rr * vpr;
+    if (l0 + rr < a.lpad) o[idx] = *reinterpret_cast<const uint4*>(Os + rr * RS + cv * 16);
+  }
+}
+
 // Layer 0, common shape (cout = 32, k = 7, stride 1, 'same' padding): 2 positions per thread, all 32 output channels in
 // packed fp32x2 accumulators (channel pairs); weights are read as broadcast float4 (4 channels of one (cin, tap)), so one
 // LDS.128 feeds 4 FFMA2 -- the kernel is FMA-pipe bound (448 FMA per position) instead of shared-memory bound.
@@ -706,7 +757,7 @@ static int plan_layer(const ConvLayer& l, LayerPlan& p, bool tf32 = false) {
 
 int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_REQUIRE(get_encode_fn() != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
-  AA_REQUIRE(layers.size() >= 2 && layers[0].stride == 1 && layers[0].cout <= 32 && layers[0].cout % 8 == 0 && layers[0].cin <= 4 &&
+  AA_REQUIRE(layers.size() >= 2 && layers[0].stride == 1 && layers[0].cout <= 64 && layers[0].cout % 8 == 0 && layers[0].cin <= 4 &&
                  layers[0].k <= 7,
              "first layer shape not supported on the tensor-core path");
   TcState* st = new TcState();
@@ -817,8 +868,10 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
       conv_l0_reg_kernel<1><<<(unsigned)std::min<long long>(l0_tiles, 2LL * aa::num_sms()), 256, kL0Smem, stream>>>(a, l0_tpr, (int)l0_tiles);
     else if (ly.cout == 32 && ly.k == 7 && ly.pad == 3)
       conv_l0_c32k7_kernel<<<dim3((unsigned)((a.lpad + kL0Pos - 1) / kL0Pos), (unsigned)batch), 256, kL0Smem, stream>>>(a);
-    else
+    else if (ly.cout <= 32)
       conv_l0_kernel<<<dim3((unsigned)((a.lpad + 255) / 256), (unsigned)batch), 256, 0, stream>>>(a);
+    else
+      conv_l0_wide_kernel<<<dim3((unsigned)((a.lpad + 127) / 128), (unsigned)batch), 128, 0, stream>>>(a);
     AA_LAUNCH_CHECK();
     l = lout;
   }

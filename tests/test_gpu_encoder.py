@@ -188,6 +188,56 @@ def test_bf16_fused_residual_units_match_layerwise(setup):
         assert rel_l2(c, b.cpu()) < 1.5e-2, (shape, rel_l2(c, b.cpu()))
 
 
+@pytest.mark.parametrize("capacity,stride", [(32, 4), (64, 2)])
+def test_bf16_fused_units_are_bit_identical_to_layerwise_in_exact_arithmetic(capacity, stride):
+    """Fused ResidualUnit kernels (C = 32 and C = 64, dilations 1 / 3 / 9) against the layer-wise tcgen05 path with operands chosen so
+    that NOTHING rounds: every conv output channel copies ONE (input channel, tap) with weight 1 (the down-conv: 1/8), inputs are
+    integers 0..3, biases 0 -> all activations are small non-negative dyadic numbers (ELU is the identity on them, bf16 holds them
+    exactly, fp32 sums of them are exact in any order).  The two paths must then agree BIT FOR BIT; a wrong tap, dilation or row
+    offset at a tile seam moves a value.  Lengths cover many 128-row tiles plus ragged tails."""
+    import os
+    import audio_algebra_b200 as aab
+
+    def build(no_fusion):
+        if no_fusion:
+            os.environ["AA_NO_RU_FUSION"] = "1"
+        try:
+            enc = aab.SoundStreamXLEncoder(in_channels=2, capacity=capacity, latent_dim=64, c_mults=[2], strides=[stride], compute_dtype="bf16")
+            with torch.no_grad():
+                for li, conv in enumerate(enc.flat_convs()):
+                    cout, cin, k = conv.weight.shape
+                    w = torch.zeros(cout, cin, k)
+                    o = torch.arange(cout)
+                    w[o, (o * 5 + li) % cin, (o + li) % k] = 0.125 if conv.stride[0] > 1 else 1.0
+                    conv.weight.copy_(w)
+                    conv.bias.zero_()
+            enc = enc.cuda()
+            enc(torch.zeros(1, 2, 512, device="cuda"))      # the handle reads the switch at its first bf16 forward
+        finally:
+            os.environ.pop("AA_NO_RU_FUSION", None)
+        return enc
+
+    fused, layerwise = build(False), build(True)
+    for shape, seed in [((2, 2, 131072), 1), ((3, 2, 5000), 2), ((1, 2, 128 * 37 + 5), 3)]:
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randint(0, 4, shape, generator=g).float()
+        a, b = fused(x.cuda()), layerwise(x.cuda())
+        assert torch.equal(a, b), (shape, (a - b).abs().max().item())
+        assert a.abs().max() > 0                             # not a trivially empty signal path
+        if shape[2] == 5000:                                 # and the exact path equals the float64 convolution of the same weights
+            ref = x.double()
+            import torch.nn.functional as F
+            convs = layerwise.flat_convs()
+            ref = F.elu(F.conv1d(ref, convs[0].weight.double().cpu(), padding=3))
+            for r in range(3):
+                c1, c2 = convs[1 + 2 * r], convs[2 + 2 * r]
+                h = F.elu(F.conv1d(ref, c1.weight.double().cpu(), padding=c1.padding[0], dilation=c1.dilation[0]))
+                ref = F.elu(ref + F.conv1d(h, c2.weight.double().cpu()))
+            ref = F.elu(F.conv1d(ref, convs[7].weight.double().cpu(), stride=stride, padding=convs[7].padding[0]))
+            ref = F.conv1d(ref, convs[8].weight.double().cpu(), padding=1)
+            assert torch.equal(a.cpu().double(), ref)
+
+
 def test_fused_fader_mix_three_and_four_stems(setup):
     "layer 0 sums up to four fader-scaled stems in its load (get_stems_faders maxstems > 2): fp32 and bf16 paths"
     aab, O, enc_o, dv = setup
@@ -287,6 +337,23 @@ def test_other_encoder_configs_on_the_tensor_core_paths(setup, in_ch, c_mults, s
         else:
             cos = torch.nn.functional.cosine_similarity(y.flatten(1).double().cpu(), yr.flatten(1).double(), dim=1)
             assert cos.min().item() >= 0.999, (mode, cos)
+
+
+def test_do_mixing_uses_the_fused_encode_and_keeps_the_archive_contract(setup):
+    "aa_mixer.do_mixing with the conv encoder: fader scaling / stem sum inside the first conv, 'mix' / 'fadedstems' built on first access"
+    aab, O, enc_o, dv = setup
+    torch.manual_seed(2)
+    aa = aab.AudioAlgebra(64, 64).cuda()
+    stems = [_x((2, 2, 4096), 31).cuda(), _x((2, 2, 4096), 32).cuda()]
+    faders = [1.4630, -0.5718]
+    dv.model.eval()
+    zsum, zmix, archive = aab.do_mixing(stems, faders, dv.model, aa, "cuda")
+    assert set(archive.keys()) == {'zs', 'mix', 'ys', 'ymix', 'ymix_recon', 'fadedstems', 'yrecons', 'ysum'} and 'mix' in archive
+    mix = faders[0] * stems[0] + faders[1] * stems[1]
+    assert rel_l2(archive['mix'], mix) < 1e-6 and rel_l2(archive['fadedstems'][1], faders[1] * stems[1]) < 1e-6
+    assert rel_l2(archive['ymix'], O.dvae_encode(enc_o, mix.cpu())) < 1e-3          # DiffusionDVAE.encode: no tanh
+    assert rel_l2(archive['ys'][0], O.dvae_encode(enc_o, (faders[0] * stems[0]).cpu())) < 1e-3
+    assert rel_l2(zsum, archive['zs'][0] + archive['zs'][1]) < 1e-6 and archive.get('nope') is None
 
 
 def test_encode_all_notebook_signature_and_npy_writer(setup, tmp_path):

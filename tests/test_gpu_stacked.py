@@ -73,3 +73,20 @@ def test_reference_shape_kat_and_setup(setup):
     assert not hasattr(w.model, "latent_encoder_ema") and not w.model.training
     with pytest.raises(NotImplementedError):
         w.decode(torch.zeros(1, 32, 4))
+
+
+def test_first_stage_on_tcgen05_bf16(setup):
+    """compute_dtype="bf16": the capacity-64 / stride-2 SoundStreamXL first stage (1.6 TFLOP per 2^18-sample chunk, 87 % of the encode)
+    runs on the tcgen05 implicit-GEMM kernels (K up to 7168: 112 K chunks per tile); BASELINE.json bf16 gate: cosine >= 0.999."""
+    aab, O, orc, m = setup
+    mb = aab.StackedDiffAEWrapper(debug=False, compute_dtype="bf16")
+    mb.first_stage_autoencoder.encoder.load_oracle_weights(orc.first)
+    mb.model.latent_encoder.load_state_dict(orc.second.state_dict())
+    mb = mb.cuda()
+    x = _x((2, 2, 16384), 5)
+    with torch.no_grad():
+        ref1, ref = torch.tanh(orc.first(x)), orc(x)
+    cos1 = torch.nn.functional.cosine_similarity(mb.first_stage_autoencoder.encode(x.cuda()).cpu().flatten(1).double(), ref1.flatten(1).double(), dim=1)
+    assert cos1.min().item() >= 0.999
+    cos = torch.nn.functional.cosine_similarity(mb.encode(x.cuda()).cpu().flatten(1).double(), ref.flatten(1).double(), dim=1)
+    assert cos.min().item() >= 0.999

@@ -22,6 +22,7 @@ for dt in ("fp32_cuda_cores", "fp32", "bf16"):
         xb = torch.rand(4, 2, 262144, device="cuda") - 0.5
         enc(xb); torch.cuda.synchronize()
         t0 = time.perf_counter(); enc(xb); torch.cuda.synchronize(); dt_s = time.perf_counter() - t0
-        print(dt, tuple(y.shape), "rel", rel, "4 x 262144:", round(dt_s * 1e3, 2), "ms")
+        cos = torch.nn.functional.cosine_similarity(y.cpu().double().flatten(1), ref.double().flatten(1), dim=1).min().item()
+        print(dt, tuple(y.shape), "rel", rel, "cos", cos, "4 x 262144:", round(dt_s * 1e3, 2), "ms")
     except Exception as e:
         print(dt, "FAILED:", repr(e)[:300])
