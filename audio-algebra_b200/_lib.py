@@ -34,6 +34,9 @@ _SIGS = {
     "aa_stft_complex_tf_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
     "aa_stft_power_tf_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
     "aa_stft_mel_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
+    "aa_stft_mel_tf_f32": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
+    "aa_stft_mel_tf_supported": (_i, [_p]),
+    "aa_stft_mel_tf_f32_host": (_i, [_p, _p, _i64, _i64, _i, _p, _i64]),
     "aa_magdphase_f32": (_i, [_p, _i64, _i64, _i64, _p, _p]),
     "aa_magdphase_ex_f32": (_i, [_p, _i64, _i64, _i64, _i, _i, _p, _p]),
     "aa_stft_mel_f32_host": (_i, [_p, _p, _i64, _i64, _i, _p, _i64]),

@@ -547,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft2048_kernel(const StftArgs a)
 }
 
 #include "stft2048_v2.cuh"
+#include "stft2048_v3.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Generic kernel: one CTA per (row, frame); M = n_fft/2 complex points in shared memory.
@@ -920,6 +921,9 @@ struct AaStftPlan {
   bool v2_mel_ok = false;        // the filterbank is a <= 2-adjacent-tap band with non-decreasing filter index
   int4* d_v2_groups = nullptr;   // warp start indices + 48-byte group records of the banded mel walk
   int v2_groups_len = 0;
+  // stft2048_v3_kernel (no inter-warp synchronisation; warp-private mel walk, [row][frame][mel] output)
+  bool v3_mel_ok = false;
+  unsigned char* d_v3_tab = nullptr;   // kV3MelTab bytes + uint32 [n_mels] run slots (see stft2048_v3.cuh)
   // resources of aa_stft_mel_f32_host (created lazily)
   cudaStream_t hstream[2] = {nullptr, nullptr};
   float* hbuf_in[2] = {nullptr, nullptr};
@@ -1027,6 +1031,72 @@ static int v2_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int 
   AA_CUDA(cudaMemcpy(p->d_v2_groups, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice));
   p->v2_mel_ok = true;
   return AA_OK;
+}
+
+// Tables of the warp-private mel walk of stft2048_v3_kernel (see the header of stft2048_v3.cuh).  The bank must be a
+// <= 2-adjacent-tap band with non-decreasing lower filter index (torchaudio's triangular HTK / Slaney banks are); runs of equal
+// m_lo are numbered in bin order (only the non-empty ones: a filter whose run is empty points at a permanent zero slot).
+static int v3_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int n_mels) {
+  p->v3_mel_ok = false;
+  if (F != 1025 || n_mels < 1 || n_mels + 2 > kV3Runs) return AA_OK;
+  std::vector<int> run(F);
+  std::vector<float2> w(F, make_float2(0.f, 0.f));
+  int prev = -1;
+  for (int k = 0; k < F; ++k) {
+    int nz[3], nn = 0;
+    for (int m = 0; m < n_mels && nn < 3; ++m)
+      if (fb[(size_t)k * n_mels + m] != 0.0f) nz[nn++] = m;
+    int m;
+    if (nn > 2) return AA_OK;
+    if (nn == 2) {
+      if (nz[1] != nz[0] + 1) return AA_OK;
+      m = nz[0];
+    } else if (nn == 1) {
+      m = (prev == nz[0] - 1) ? prev : nz[0];
+    } else {
+      m = prev;
+    }
+    if (m < prev) return AA_OK;
+    run[k] = m + 1;
+    prev = m;
+    w[k].x = (m >= 0) ? 0.25f * fb[(size_t)k * n_mels + m] : 0.f;          // P holds 4 |X|^2
+    w[k].y = (m + 1 < n_mels) ? 0.25f * fb[(size_t)k * n_mels + m + 1] : 0.f;
+  }
+  std::vector<int> slot(F), slot_of_run(n_mels + 1, kV3Runs - 1);
+  int c = 0;
+  for (int k = 0; k < F; ++k) {
+    if (k > 0 && run[k] != run[k - 1]) ++c;
+    slot[k] = c;
+    slot_of_run[run[k]] = c;
+  }
+  if (c + 1 > kV3Runs - 1) return AA_OK;
+  std::vector<unsigned char> tab(kV3MelTab + 4 * (size_t)n_mels, 0);
+  float2* tw = reinterpret_cast<float2*>(tab.data());
+  uint32_t* masks = reinterpret_cast<uint32_t*>(tab.data() + 32 * 256);
+  uint32_t* first = reinterpret_cast<uint32_t*>(tab.data() + 32 * 256 + 128);
+  for (int g = 0; g < 32; ++g) {
+    uint32_t mk = 0;
+    for (int t = 0; t < 32; ++t) {
+      const int k = 32 * g + t;
+      tw[t * 32 + g] = w[k];
+      if (run[k + 1] != run[k]) mk |= 1u << t;
+    }
+    masks[g] = mk;
+    first[g] = (uint32_t)slot[32 * g];
+    if (g >= 1 && g <= 30 && mk == 0) return AA_OK;   // a segment without a run end: tail targets would collide
+  }
+  *reinterpret_cast<float2*>(tab.data() + 32 * 256 + 256) = w[1024];
+  uint32_t* filt = reinterpret_cast<uint32_t*>(tab.data() + kV3MelTab);
+  for (int m = 0; m < n_mels; ++m) filt[m] = (uint32_t)slot_of_run[m + 1] | ((uint32_t)slot_of_run[m] << 16);
+  AA_CUDA(cudaMalloc(&p->d_v3_tab, tab.size()));
+  AA_CUDA(cudaMemcpy(p->d_v3_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+  p->v3_mel_ok = true;
+  return AA_OK;
+}
+
+static int v3_smem_bytes(int mode, int n_mels) {
+  const int mel_bytes = mode == MODE_MEL ? ((kV3MelTab + 4 * n_mels + 15) & ~15) + kV3W * 2 * kV3Runs * 8 : 0;
+  return kV3W * kV3Xb + kV3Tables + mel_bytes + 16;
 }
 
 static int v2_smem_bytes(int nbuf, int hop, int groups_len) {
@@ -1216,6 +1286,8 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
                          cudaMemcpyHostToDevice));
       rc = v2_build_mel(p, fb, F, n_mels);
       if (rc != AA_OK) return rc;
+      rc = v3_build_mel(p, fb, F, n_mels);
+      if (rc != AA_OK) return rc;
     }
   }
   if (p->fast) {
@@ -1241,6 +1313,7 @@ int aa_stft_plan_destroy(AaStftPlan* p) {
   if (!p) return AA_OK;
   cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4); cudaFree(p->d_mel_steps); cudaFree(p->d_lane_consts); cudaFree(p->d_wk);
   cudaFree(p->d_v2_groups);
+  cudaFree(p->d_v3_tab);
   for (int i = 0; i < 2; ++i) {
     if (p->hbuf_in[i]) cudaFree(p->hbuf_in[i]);
     if (p->hbuf_out[i]) cudaFree(p->hbuf_out[i]);
@@ -1289,6 +1362,33 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
   a.mel_w4 = p->d_mel_w4; a.out = out; a.out_tf = out_tf;
   a.wav_aligned16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0) ? 1 : 0;
   const bool big_out = rows * (int64_t)std::max(p->n_freq, p->n_mels) * n_frames >= (1LL << 31);
+  const int v3_mode = getenv("AA_STFT_V3") ? atoi(getenv("AA_STFT_V3")) : 1;      // 0: older kernels only
+  AA_REQUIRE(!(mode == MODE_MEL && out_tf) || (p->fast && p->v3_mel_ok && !big_out),
+             "the [row][frame][mel] layout needs n_fft = 2048 with a Hann window and a banded filterbank (aa_stft_mel_tf_supported)");
+  if (p->fast && !big_out && out_tf && (v3_mode || mode == MODE_MEL) && rows < (1LL << 30) && n_pad < (1LL << 30)) {
+    Stft3Args b;
+    b.wav = wav; b.out = out; b.rows = (int)rows; b.n_in = (int)n_in; b.n_pad = (int)n_pad; b.n_frames = (int)n_frames;
+    b.hop = p->hop; b.center_off = a.center_off;
+    const int64_t ni = ((rows + 1) / 2) * n_frames;
+    AA_REQUIRE(ni < (1LL << 31) - 4096 * kV3W, "problem too large for the fast STFT path");
+    b.n_items = (int)ni; b.n_freq = p->n_freq; b.n_mels = p->n_mels;
+    b.wav_ok8 = ((reinterpret_cast<uintptr_t>(wav) & 7) == 0 && (n_in & 1) == 0 && (p->hop & 1) == 0) ? 1 : 0;
+    static const int v3_prefetch = getenv("AA_STFT_PREFETCH") ? atoi(getenv("AA_STFT_PREFETCH")) : 1;
+    b.prefetch = v3_prefetch;
+    b.tw1 = p->d_tw1; b.lane_consts = p->d_lane_consts; b.mel_tab = p->d_v3_tab;
+    const int smem = v3_smem_bytes(mode, p->n_mels);
+    const int64_t tiles = (ni + kV3W - 1) / kV3W;
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)aa::num_sms());
+#define AA_V3(MD)                                                               \
+  do {                                                                          \
+    AA_CUDA(aa::ensure_dyn_smem(stft2048_v3_kernel<MD>, smem));                 \
+    stft2048_v3_kernel<MD><<<grid, kV3W * 32, smem, st>>>(b);                   \
+  } while (0)
+    if (mode == MODE_COMPLEX) AA_V3(MODE_COMPLEX); else if (mode == MODE_POWER) AA_V3(MODE_POWER); else AA_V3(MODE_MEL);
+#undef AA_V3
+    AA_LAUNCH_CHECK();
+    return AA_OK;
+  }
   const int v2_mode = getenv("AA_STFT_V2") ? atoi(getenv("AA_STFT_V2")) : 1;       // 0: v1 kernel only
   static const int v2_nbuf = getenv("AA_STFT_NBUF") ? atoi(getenv("AA_STFT_NBUF")) : 1;     // sample ring depth wanted (1 or 2)
   // mel: the v2 kernel's banded walk is correct but still slower end to end than the v1 tile kernel (393 vs 375 us on the headline
@@ -1405,6 +1505,12 @@ int aa_stft_mel_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int6
   return stft_launch(plan, MODE_MEL, wav, rows, n_in, zero_pad, out, (cudaStream_t)stream);
 }
 
+int aa_stft_mel_tf_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                       float* out, void* stream) {
+  return stft_launch(plan, MODE_MEL, wav, rows, n_in, zero_pad, out, (cudaStream_t)stream, 1);
+}
+int aa_stft_mel_tf_supported(const AaStftPlan* plan) { return (plan && plan->fast && plan->v3_mel_ok) ? 1 : 0; }
+
 int aa_magdphase_f32(const float* spec, int64_t c, int64_t n_freq, int64_t n_frames, float* out, void* stream) {
   AA_REQUIRE(spec && out, "NULL tensor pointer");
   AA_REQUIRE(c >= 1 && n_freq >= 1 && n_frames >= 1 && n_frames < (1LL << 31), "bad shape");
@@ -1415,8 +1521,8 @@ int aa_magdphase_f32(const float* spec, int64_t c, int64_t n_freq, int64_t n_fra
   return AA_OK;
 }
 
-int aa_stft_mel_f32_host(const AaStftPlan* plan_c, const float* wav_host, int64_t rows, int64_t n_in, int zero_pad,
-                         float* out_host, int64_t rows_per_chunk) {
+static int mel_host_impl(const AaStftPlan* plan_c, const float* wav_host, int64_t rows, int64_t n_in, int zero_pad,
+                         float* out_host, int64_t rows_per_chunk, int out_tf) {
   AaStftPlan* p = const_cast<AaStftPlan*>(plan_c);
   AA_REQUIRE(p != nullptr && wav_host && out_host, "NULL argument");
   AA_REQUIRE(p->n_mels > 0, "plan was created without a mel stage");
@@ -1443,7 +1549,7 @@ int aa_stft_mel_f32_host(const AaStftPlan* plan_c, const float* wav_host, int64_
     const int64_t nr = std::min<int64_t>(rows_per_chunk, rows - r0);
     cudaStream_t st = p->hstream[slot];
     AA_CUDA(cudaMemcpyAsync(p->hbuf_in[slot], wav_host + r0 * n_in, sizeof(float) * nr * n_in, cudaMemcpyHostToDevice, st));
-    rc = stft_launch(p, MODE_MEL, p->hbuf_in[slot], nr, n_in, zero_pad, p->hbuf_out[slot], st);
+    rc = stft_launch(p, MODE_MEL, p->hbuf_in[slot], nr, n_in, zero_pad, p->hbuf_out[slot], st, out_tf);
     if (rc != AA_OK) return rc;
     AA_CUDA(cudaMemcpyAsync(out_host + r0 * out_per_row, p->hbuf_out[slot], sizeof(float) * nr * out_per_row,
                             cudaMemcpyDeviceToHost, st));
@@ -1451,6 +1557,15 @@ int aa_stft_mel_f32_host(const AaStftPlan* plan_c, const float* wav_host, int64_
   AA_CUDA(cudaStreamSynchronize(p->hstream[0]));
   AA_CUDA(cudaStreamSynchronize(p->hstream[1]));
   return AA_OK;
+}
+
+int aa_stft_mel_f32_host(const AaStftPlan* plan, const float* wav_host, int64_t rows, int64_t n_in, int zero_pad,
+                         float* out_host, int64_t rows_per_chunk) {
+  return mel_host_impl(plan, wav_host, rows, n_in, zero_pad, out_host, rows_per_chunk, 0);
+}
+int aa_stft_mel_tf_f32_host(const AaStftPlan* plan, const float* wav_host, int64_t rows, int64_t n_in, int zero_pad,
+                            float* out_host, int64_t rows_per_chunk) {
+  return mel_host_impl(plan, wav_host, rows, n_in, zero_pad, out_host, rows_per_chunk, 1);
 }
 
 #pragma GCC visibility pop

@@ -147,6 +147,9 @@ class _StftPlan:
         check(lib.aa_stft_out_shape(self.handle, int(n_in), int(bool(zero_pad)), C.byref(n_pad), C.byref(n_frames)))
         return n_pad.value, n_frames.value
 
+    def mel_tf_supported(self):
+        return bool(lib.aa_stft_mel_tf_supported(self.handle))
+
 
 class _StftFrontEnd(GivenModelClass):
     """Shared plumbing of the three STFT encoders.  torchaudio kwargs understood: win_length,
@@ -211,10 +214,10 @@ class _StftFrontEnd(GivenModelClass):
         return self._plans[device_index]
 
     def _run(self, waveform, mode, out=None, freq_major=False):
-        """waveform [..., N] float32 -> [..., F|n_mels, T].  Complex and power spectrograms come back as the transposed view of a
-        [..., T, F] buffer -- exactly what torch.stft / torchaudio.transforms.Spectrogram return (same shape, values AND strides
-        as the reference's tensors), and the layout the kernels write at full sector width; freq_major=True asks for a
-        contiguous [..., F, T] tensor instead.  CUDA input: stream-ordered kernel on the
+        """waveform [..., N] float32 -> [..., F|n_mels, T].  Spectrograms come back as the transposed view of a
+        [..., T, F|n_mels] buffer -- exactly what torch.stft / torchaudio.transforms.Spectrogram / MelScale return (same shape,
+        values AND strides as the reference's tensors), and the layout the kernels write at full sector width (mel: when the plan
+        supports it, i.e. n_fft = 2048, Hann, triangular bank); freq_major=True asks for a contiguous [..., F, T] tensor instead.  CUDA input: stream-ordered kernel on the
         current stream.  CPU input: H2D, kernel, D2H (result returned on the CPU, like the reference
         keeps the input's device) -- the mel variant pipelines the copies in chunks; `out` may be a
         preallocated (ideally pinned) CPU tensor, as in the reference's bulk-encode loop
@@ -230,14 +233,21 @@ class _StftFrontEnd(GivenModelClass):
         n_pad, n_frames = plan.out_shape(n_in, self.zero_pad)
         bins = self.n_mels if mode == "mel" else self.n_fft // 2 + 1
         with torch.cuda.device(dev):
+            mel_tf = mode == "mel" and not freq_major and plan.mel_tf_supported()
             if on_cpu and mode == "mel":
                 x = waveform.contiguous()
                 shape = (*lead, bins, n_frames)
                 if out is None:
-                    out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-                elif tuple(out.shape) != shape or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
-                    raise ValueError(f"out must be a contiguous float32 CPU tensor of shape {shape}")
-                check(lib.aa_stft_mel_f32_host(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), 64))
+                    out = (torch.empty((*lead, n_frames, bins), dtype=torch.float32, pin_memory=True).transpose(-1, -2) if mel_tf
+                           else torch.empty(shape, dtype=torch.float32, pin_memory=True))
+                elif tuple(out.shape) != shape or out.dtype != torch.float32 or out.is_cuda:
+                    raise ValueError(f"out must be a float32 CPU tensor of shape {shape}")
+                if out.is_contiguous():
+                    check(lib.aa_stft_mel_f32_host(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), 64))
+                elif mel_tf and out.transpose(-1, -2).is_contiguous():   # the reference's own layout: a [.., mel, T] view of [.., T, mel]
+                    check(lib.aa_stft_mel_tf_f32_host(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), 64))
+                else:
+                    raise ValueError("out must be contiguous, or the transposed view of a contiguous [..., frames, n_mels] tensor")
                 return out
             x = waveform.to(f"cuda:{dev}", non_blocking=True).contiguous()
             if mode in ("complex", "power") and not freq_major:
@@ -251,6 +261,10 @@ class _StftFrontEnd(GivenModelClass):
             elif mode == "power":
                 out = torch.empty((*lead, bins, n_frames), dtype=torch.float32, device=x.device)
                 check(lib.aa_stft_power_f32(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), stream_ptr()))
+            elif mel_tf:
+                out = torch.empty((*lead, n_frames, bins), dtype=torch.float32, device=x.device)
+                check(lib.aa_stft_mel_tf_f32(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), stream_ptr()))
+                out = out.transpose(-1, -2)
             else:
                 out = torch.empty((*lead, bins, n_frames), dtype=torch.float32, device=x.device)
                 check(lib.aa_stft_mel_f32(plan.handle, ptr(x), rows, n_in, int(self.zero_pad), ptr(out), stream_ptr()))
@@ -309,7 +323,7 @@ class MelSpectrogramAE(_StftFrontEnd):
         self.sample_rate = sample_rate
 
     def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
-        return self._run(waveform, "mel", out=kwargs.get("out"))
+        return self._run(waveform, "mel", out=kwargs.get("out"), freq_major=bool(kwargs.get("freq_major", False)))
 
 
 class DVAEWrapper(GivenModelClass):

@@ -86,6 +86,14 @@ int aa_stft_power_tf_f32(const AaStftPlan* plan, const float* wav, int64_t rows,
 /* -> out [rows][n_mels][n_frames] f32 */
 int aa_stft_mel_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
                     float* out, void* stream);
+/* The mel spectrogram written mel-minor: out [rows][n_frames][n_mels].  Again the reference's own memory layout: torchaudio's
+ * MelScale returns matmul(spec^T, fb)^T, i.e. MelSpectrogramAE.encode (given_models.py:267,277) hands back a [.., n_mels, time]
+ * VIEW of a [.., time, n_mels] buffer (strides (.., 1, n_mels)).  One warp produces all n_mels values of a (row, frame) and
+ * writes them as one contiguous line.  Needs n_fft = 2048 with the Hann window and a triangular (<= 2 adjacent taps per bin)
+ * filterbank: aa_stft_mel_tf_supported() returns 1 when the plan can run it, else callers use aa_stft_mel_f32. */
+int aa_stft_mel_tf_f32(const AaStftPlan* plan, const float* wav, int64_t rows, int64_t n_in, int zero_pad,
+                       float* out, void* stream);
+int aa_stft_mel_tf_supported(const AaStftPlan* plan);
 /* MagDPhaseSpectrogramAE.encode epilogue (given_models.py:214-231, use_cos=False): spec [c][F][T]
  * complex64 -> out [2c][F][T] f32: magnitudes then phase differences along T (negative differences
  * wrapped by +2*3.141592653589, frame 0 keeps the phase). */
@@ -95,6 +103,9 @@ int aa_magdphase_f32(const float* spec, int64_t c, int64_t n_freq, int64_t n_fra
  * should be pinned for full PCIe bandwidth (pageable memory works, slower). */
 int aa_stft_mel_f32_host(const AaStftPlan* plan, const float* wav_host, int64_t rows, int64_t n_in, int zero_pad,
                          float* out_host, int64_t rows_per_chunk);
+/* same, out_host [rows][n_frames][n_mels] (the layout of aa_stft_mel_tf_f32) */
+int aa_stft_mel_tf_f32_host(const AaStftPlan* plan, const float* wav_host, int64_t rows, int64_t n_in, int zero_pad,
+                            float* out_host, int64_t rows_per_chunk);
 
 /* ------------------------------------------------------------------------------------------
  * Latent algebra (aa_mixer.py:307 zsum; train_aa_effects.py:70-71 guesses; Destructo.ipynb

@@ -276,16 +276,44 @@ def test_v2_kernel_banded_mel_and_v1_kernels_agree_with_the_oracle(aab, monkeypa
     g = torch.Generator().manual_seed(hop + n)
     x = torch.rand(*rows, n, generator=g) - 0.5
     ref = O.mel_spectrogram(x, 48000, 2048, hop)
-    for v2_mel in ("0", "1"):
+    mel = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=hop)
+    y3 = mel.encode(x.cuda())                     # stft2048_v3_kernel: warp-private walk, [row][frame][mel] buffer
+    assert tuple(y3.shape) == tuple(ref.shape) and rel_l2(y3, ref) < 1e-5, "mel, v3 kernel"
+    if hop % 4 == 0:
+        assert y3.stride()[-2:] == (1, 128), "the v3 kernel returns torchaudio's own layout (a transposed view)"
+    for v2_mel in ("0", "1"):                     # contiguous [.., mel, T] output: v1 tile kernel / v2 kernel with the banded walk
         monkeypatch.setenv("AA_STFT_V2_MEL", v2_mel)
-        y = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=hop).encode(x.cuda())
-        assert tuple(y.shape) == tuple(ref.shape)
+        y = mel.encode(x.cuda(), freq_major=True)
+        assert tuple(y.shape) == tuple(ref.shape) and y.is_contiguous()
         assert rel_l2(y, ref) < 1e-5, f"mel, AA_STFT_V2_MEL={v2_mel}"
+        assert rel_l2(y, y3) < 2e-6
     refp = O.power_spectrogram(x, 2048, hop) if hasattr(O, "power_spectrogram") else None
-    for v2 in ("0", "1"):
+    for v3, v2 in (("1", "1"), ("0", "1"), ("0", "0")):
+        monkeypatch.setenv("AA_STFT_V3", v3)
         monkeypatch.setenv("AA_STFT_V2", v2)
         yp = aab.MagSpectrogramAE(n_fft=2048, hop_length=hop).encode(x.cuda())
         yc = aab.SpectrogramAE(n_fft=2048, hop_length=hop).encode(x.cuda())
         assert rel_l2(yc.abs() ** 2, yp) < 1e-5
         if refp is not None:
-            assert rel_l2(yp, refp) < 1e-5, f"power, AA_STFT_V2={v2}"
+            assert rel_l2(yp, refp) < 1e-5, f"power, AA_STFT_V3={v3} AA_STFT_V2={v2}"
+
+
+def test_mel_layout_matches_torchaudio(aab):
+    """torchaudio's MelScale returns matmul(spec^T, fb)^T: the reference's mel tensors are [.., n_mels, T] VIEWS of a
+    [.., T, n_mels] buffer.  The n_fft = 2048 front-end reproduces shape, values and strides; host input with a preallocated
+    result in either layout (the reference's bulk loop preallocates) goes through the matching C entry point."""
+    import torchaudio
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(5, 2, 24000, generator=g) - 0.5
+    ref = torchaudio.transforms.MelSpectrogram(sample_rate=48000, n_fft=2048, hop_length=512)(x)
+    mel = aab.MelSpectrogramAE(sample_rate=48000, n_fft=2048, hop_length=512)
+    mel.zero_pad = False
+    y = mel.encode(x.cuda())
+    assert tuple(y.shape) == tuple(ref.shape) and y.stride() == ref.stride() and rel_l2(y, ref) < TOL
+    yh = mel.encode(x)                                     # host in, host out (pinned), same layout
+    assert yh.device.type == "cpu" and yh.stride() == ref.stride() and rel_l2(yh, ref) < TOL
+    out_c = torch.empty(tuple(ref.shape), pin_memory=True)                                   # contiguous [.., mel, T]
+    out_t = torch.empty(5, 2, ref.shape[-1], 128, pin_memory=True).transpose(-1, -2)         # torchaudio's layout
+    assert mel.encode(x, out=out_c) is out_c and rel_l2(out_c, ref) < TOL
+    assert mel.encode(x, out=out_t) is out_t and rel_l2(out_t, ref) < TOL
+    assert torch.equal(out_t, yh)

@@ -13,14 +13,15 @@ for name, cls in [("mel", aab.MelSpectrogramAE), ("power", aab.MagSpectrogramAE)
         continue
     kw = dict(sample_rate=48000) if name == "mel" else {}
     m = cls(n_fft=2048, hop_length=int(os.environ.get("HOP", 512)), center=os.environ.get("CENTER", "1") == "1", **kw)
+    ekw = dict(freq_major=True) if (name == "mel" and os.environ.get("FREQ_MAJOR")) else {}
     for _ in range(3):
-        out = m.encode(x)
+        out = m.encode(x, **ekw)
     torch.cuda.synchronize()
     ts = []
     for _ in range(10):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); out = m.encode(x); e1.record()
+        e0.record(); out = m.encode(x, **ekw); e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     ts.sort()
