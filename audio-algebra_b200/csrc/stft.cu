@@ -1095,7 +1095,7 @@ static int v3_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int 
 }
 
 static int v3_smem_bytes(int mode, int n_mels) {
-  const int mel_bytes = mode == MODE_MEL ? ((kV3MelTab + 4 * n_mels + 15) & ~15) + kV3W * 2 * kV3Runs * 8 : 0;
+  const int mel_bytes = mode == MODE_MEL ? ((kV3MelTab + 4 * n_mels + 15) & ~15) + kV3W * kV3Runs * 16 : 0;
   return kV3W * kV3Xb + kV3Tables + mel_bytes + 16;
 }
 
@@ -1373,6 +1373,7 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
     AA_REQUIRE(ni < (1LL << 31) - 4096 * kV3W, "problem too large for the fast STFT path");
     b.n_items = (int)ni; b.n_freq = p->n_freq; b.n_mels = p->n_mels;
     b.wav_ok8 = ((reinterpret_cast<uintptr_t>(wav) & 7) == 0 && (n_in & 1) == 0 && (p->hop & 1) == 0) ? 1 : 0;
+    b.wav_ok16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0 && (n_in & 3) == 0 && (p->hop & 3) == 0) ? 1 : 0;
     static const int v3_prefetch = getenv("AA_STFT_PREFETCH") ? atoi(getenv("AA_STFT_PREFETCH")) : 1;
     b.prefetch = v3_prefetch;
     b.tw1 = p->d_tw1; b.lane_consts = p->d_lane_consts; b.mel_tab = p->d_v3_tab;

@@ -34,7 +34,7 @@ struct Stft3Args {
   float* out;
   int rows, n_in, n_pad, n_frames, hop, center_off;
   int n_items;               // row pairs x frames
-  int n_freq, n_mels, wav_ok8, prefetch;
+  int n_freq, n_mels, wav_ok8, wav_ok16, prefetch;
   const float2* tw1;         // [32][32] W_1024^(k1 n2)
   const float* lane_consts;  // float4[32] Hann phases + float2[32] W_2048^lane
   const unsigned char* mel_tab;   // kV3MelTab bytes (see above), then uint32 [n_mels]: run slot of L | run slot of H << 16
@@ -48,7 +48,68 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
 __device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+
+// The warp-private banded mel walk over the power line in `xb_raw` (see the header): lane g = bins 32 g .. 32 g + 31.
+__device__ __forceinline__ void v3_mel_walk(const Stft3Args& a, unsigned char* xb_raw, const unsigned char* s_mel, float4* s_runs,
+                                            int lane, long long rowA, int frame, bool hasB) {
+  // ---- the warp's own banded mel walk: lane g = bins 32 g .. 32 g + 31
+  const uint32_t runs = smem_u32(s_runs);
+  const uint32_t wbase = smem_u32(s_mel) + (uint32_t)lane * 8u;
+  const uint32_t pbase = smem_u32(xb_raw) + (uint32_t)lane * (33u * 8u);
+  const uint32_t mask = reinterpret_cast<const uint32_t*>(s_mel + 32 * 256)[lane];
+  uint32_t mp = runs + reinterpret_cast<const uint32_t*>(s_mel + 32 * 256 + 128)[lane] * 16u;
+  // One step = one bin: (L, H) += P * (w_lo, w_hi); a bin that closes a run stores (L, H) of both rows with one 128-bit store,
+  // advances the run pointer and clears the sums (64-bit clears).
+  unsigned long long aL = 0ull, aH = 0ull;   // packed (rowA, rowB) fp32 pairs
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    const float2 P = lds_f2(pbase + (uint32_t)t * 8u);
+    const float2 w = lds_f2(wbase + (uint32_t)t * 256u);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(aL) : "l"(*reinterpret_cast<const unsigned long long*>(&P)), "l"(pack2(w.x, w.x)));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(aH) : "l"(*reinterpret_cast<const unsigned long long*>(&P)), "l"(pack2(w.y, w.y)));
+    if (mask & (1u << t)) {
+      asm volatile("st.shared.b64 [%0], %1;" ::"r"(mp), "l"(aL) : "memory");
+      asm volatile("st.shared.b64 [%0+8], %1;" ::"r"(mp), "l"(aH) : "memory");
+      mp += 16u;
+      aL = 0ull;
+      aH = 0ull;
+    }
+  }
+  float2 aLf, aHf;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(aLf.x), "=f"(aLf.y) : "l"(aL));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(aHf.x), "=f"(aHf.y) : "l"(aH));
+  const bool open_tail = (mask >> 31) == 0;   // my last bin did not close its run
+  if (lane == 31) {   // bin 1024 closes the last run
+    const float2 P = lds_f2(smem_u32(xb_raw) + 1056u * 8u);
+    const float2 w = *reinterpret_cast<const float2*>(s_mel + 32 * 256 + 256);
+    const float2 fL = open_tail ? pfma(P, w.x, aLf) : pmuls(P, w.x), fH = open_tail ? pfma(P, w.y, aHf) : pmuls(P, w.y);
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(mp), "f"(fL.x), "f"(fL.y), "f"(fH.x), "f"(fH.y) : "memory");
+  }
+  __syncwarp();
+  if (lane < 31 && open_tail) {   // the unfinished run at the end of my segment was stored by the lane it ends in
+    const float4 v = lds_f4(mp);
+    const float2 nL = padd(make_float2(v.x, v.y), aLf), nH = padd(make_float2(v.z, v.w), aHf);
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(mp), "f"(nL.x), "f"(nL.y), "f"(nH.x), "f"(nH.y) : "memory");
+  }
+  __syncwarp();
+  const uint32_t* s_filt = reinterpret_cast<const uint32_t*>(s_mel + kV3MelTab);
+  float* oA = a.out + ((size_t)rowA * (size_t)a.n_frames + (size_t)frame) * (size_t)a.n_mels;
+  float* oB = oA + (size_t)a.n_frames * (size_t)a.n_mels;
+  for (int m = lane; m < a.n_mels; m += 32) {
+    const uint32_t f = s_filt[m];
+    const float2 v = padd(lds_f2(runs + (f & 0xffffu) * 16u), lds_f2(runs + (f >> 16) * 16u + 8u));
+    oA[m] = v.x;
+    if (hasB) oB[m] = v.y;
+  }
+  __syncwarp();   // run arrays and P line are consumed before the buffer is reused
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_constant__ Stft3Args a) {
@@ -64,14 +125,14 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_
   float2* s_tw2l = reinterpret_cast<float2*>(s_lane + 32);
   unsigned char* s_mel = reinterpret_cast<unsigned char*>(s_tw2l + 32);    // kV3MelTab bytes + filter slots (mel mode only)
   const int mel_bytes = (MODE == MODE_MEL) ? kV3MelTab + 4 * a.n_mels : 0;
-  float2* s_runs = reinterpret_cast<float2*>(s_mel + ((mel_bytes + 15) & ~15)) + warp * (2 * kV3Runs);   // L[kV3Runs], H[kV3Runs]
+  float4* s_runs = reinterpret_cast<float4*>(s_mel + ((mel_bytes + 15) & ~15)) + warp * kV3Runs;   // (L rowA, L rowB, H rowA, H rowB) per run
 
   for (int i = tid; i < 32 * 32; i += kV3W * 32) s_tw1[i] = __ldg(a.tw1 + i);
   if (tid < 48) reinterpret_cast<float4*>(s_lane)[tid] = __ldg(reinterpret_cast<const float4*>(a.lane_consts) + tid);
   if (MODE == MODE_MEL) {
     for (int i = tid; i < mel_bytes / 4; i += kV3W * 32)
       reinterpret_cast<uint32_t*>(s_mel)[i] = __ldg(reinterpret_cast<const uint32_t*>(a.mel_tab) + i);
-    for (int i = lane; i < 2 * kV3Runs; i += 32) s_runs[i] = make_float2(0.f, 0.f);
+    for (int i = lane; i < kV3Runs; i += 32) s_runs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int i = lane; i < kV3Xb / 8; i += 32) XB[i] = make_float2(0.f, 0.f);
   __syncthreads();
@@ -90,18 +151,16 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_
     const int sf = frame * hop - a.center_off;
     const float* __restrict__ pa = a.wav + (size_t)rowA * (size_t)a.n_in;
     const bool fast = hasB && a.wav_ok8 && sf >= 0 && sf + 2048 <= a.n_in;
-    if (a.prefetch) {   // the lines of this warp's next frame: 2 rows x 64 lines
+    if (a.prefetch && lane == 0) {   // the part of this warp's NEXT frame nobody has touched yet -> L2, through the TMA unit (no LSU traffic)
       const int nitem = item + stride_items;
       if (nitem < a.n_items) {
         const int np = nitem / a.n_frames;
         const int nf = nitem - np * a.n_frames;
-        const int nsf = nf * hop - a.center_off;
-        if (nsf >= 0 && nsf + 2048 <= a.n_in && 2 * np + 1 < a.rows) {
-          const float* q = a.wav + (size_t)(2 * np) * (size_t)a.n_in + nsf;
-          prefetch_l2(q + 32 * lane);
-          prefetch_l2(q + 32 * lane + 1024);
-          prefetch_l2(q + a.n_in + 32 * lane);
-          prefetch_l2(q + a.n_in + 32 * lane + 1024);
+        const int ns = nf * hop - a.center_off + 2048 - hop;   // the last hop samples of the frame
+        if (ns >= 0 && ns + hop <= a.n_in && a.wav_ok16 && 2 * np + 1 < a.rows) {
+          const float* q = a.wav + (size_t)(2 * np) * (size_t)a.n_in + ns;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(hop * 4) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q + a.n_in), "r"(hop * 4) : "memory");
         }
       }
     }
@@ -223,49 +282,7 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_
       }
       if (lane == 0) sts_f2(smem_u32(xb_raw) + 528u * 8u, pmuls(pfma2(z16i, z16i, pmul(z16r, z16r)), 4.f));   // bin 512
       __syncwarp();
-      // ---- the warp's own banded mel walk: lane g = bins 32 g .. 32 g + 31
-      const uint32_t runs = smem_u32(s_runs);
-      const uint32_t wbase = smem_u32(s_mel) + (uint32_t)lane * 8u;
-      const uint32_t pbase = smem_u32(xb_raw) + (uint32_t)lane * (33u * 8u);
-      const uint32_t mask = reinterpret_cast<const uint32_t*>(s_mel + 32 * 256)[lane];
-      uint32_t mp = runs + reinterpret_cast<const uint32_t*>(s_mel + 32 * 256 + 128)[lane] * 8u;
-      float2 aL = make_float2(0.f, 0.f), aH = aL;
-#pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const float2 P = lds_f2(pbase + (uint32_t)t * 8u);
-        const float2 w = lds_f2(wbase + (uint32_t)t * 256u);
-        aL = pfma(P, w.x, aL);
-        aH = pfma(P, w.y, aH);
-        if (mask & (1u << t)) {
-          sts_f2(mp, aL);
-          sts_f2(mp + kV3Runs * 8u, aH);
-          mp += 8u;
-          aL = make_float2(0.f, 0.f);
-          aH = aL;
-        }
-      }
-      if (lane == 31) {   // bin 1024 closes the last run
-        const float2 P = lds_f2(smem_u32(xb_raw) + 1056u * 8u);
-        const float2 w = *reinterpret_cast<const float2*>(s_mel + 32 * 256 + 256);
-        sts_f2(mp, pfma(P, w.x, aL));
-        sts_f2(mp + kV3Runs * 8u, pfma(P, w.y, aH));
-      }
-      __syncwarp();
-      if (lane < 31) {   // the unfinished run at the end of my segment was stored by the lane it ends in
-        sts_f2(mp, padd(lds_f2(mp), aL));
-        sts_f2(mp + kV3Runs * 8u, padd(lds_f2(mp + kV3Runs * 8u), aH));
-      }
-      __syncwarp();
-      const uint32_t* s_filt = reinterpret_cast<const uint32_t*>(s_mel + kV3MelTab);
-      float* oA = a.out + ((size_t)rowA * (size_t)a.n_frames + (size_t)frame) * (size_t)a.n_mels;
-      float* oB = oA + (size_t)a.n_frames * (size_t)a.n_mels;
-      for (int m = lane; m < a.n_mels; m += 32) {
-        const uint32_t f = s_filt[m];
-        const float2 v = padd(lds_f2(runs + (f & 0xffffu) * 8u), lds_f2(runs + kV3Runs * 8u + (f >> 16) * 8u));
-        oA[m] = v.x;
-        if (hasB) oB[m] = v.y;
-      }
-      __syncwarp();   // run arrays and P line are consumed before the next frame reuses them
+      v3_mel_walk(a, xb_raw, s_mel, s_runs, lane, rowA, frame, hasB);
     } else {
       // complex / power, frequency-minor output [row][frame][1025]: stored straight from registers
       const long long e0 = (rowA * (long long)a.n_frames + frame) * a.n_freq;
