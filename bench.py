@@ -482,8 +482,10 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers (H2D + kernel + D2H inside the timed region) ----
     xh = x.cpu().pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
-    oh = torch.empty(tuple(out.shape), dtype=torch.float32, pin_memory=True)   # preallocated result buffer, like the
-    mel.encode(xh, out=oh)                                   # reference's bulk-encode loop; warm-up allocates staging
+    # preallocated (pinned) result buffer, like the reference's bulk-encode loop, in the layout the reference's own mel tensors
+    # have: a [.., n_mels, T] view of a [.., T, n_mels] buffer (torchaudio MelScale returns matmul(spec^T, fb)^T)
+    oh = torch.empty(tuple(out.shape[:-2]) + (out.shape[-1], out.shape[-2]), dtype=torch.float32, pin_memory=True).transpose(-1, -2)
+    mel.encode(xh, out=oh)                                   # warm-up allocates staging
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -516,20 +518,20 @@ def run_ours(args):
                        "l2": "inputs (268 MB per step) exceed the 126 MB L2; no extra flush"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": BATCH * 2 * CHUNK * 4,
                     "d2h_bytes_per_step": BATCH * 2 * N_MELS * (1 + CHUNK // HOP) * 4,
-                    "api": "MelSpectrogramAE.encode(pinned CPU tensor) -> aa_stft_mel_f32_host (chunked, copies overlapped)",
+                    "api": "MelSpectrogramAE.encode(pinned CPU tensor, out=pinned) -> aa_stft_mel_tf_f32_host (chunked, copies overlapped)",
                     "host_copy_ceiling": copy_ceiling, "frac_of_host_copy_ceiling": e2e_val / copy_ceiling,
                     "host_copy_GBps_per_rank": (h2d_b + d2h_b) / t_copy / 1e9,
                     "host_copy_note": "every rank copies the step's H2D and D2H bytes concurrently from / to pinned memory, no kernel; max over ranks",
                     "numa_nodes": numa_node_count(), "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "kernel": "stft2048_kernel<MEL>", "kernel_us": 1e3 * k_ms,
+                         "traffic": ncu_traffic(), "kernel": "stft2048_v3_kernel<MEL>", "kernel_us": 1e3 * k_ms,
                          "algorithmic_bytes": ALG_BYTES, "peak_source": peak_src,
                          # SURVEY.md 8d asks for the FP32 view next to the (judged) HBM view: 131 584 frame-channels x
                          # (56 kFLOP real FFT + 3 k power + 4 k sparse mel) = 8.29 GFLOP against 148 SM x 128 lanes x 2 x 1.965 GHz
                          "fp32_tflops": 8.29e9 * (BATCH / 256) / (k_ms * 1e-3) / 1e12, "fp32_peak_tflops": 74.46,
                          "fp32_frac": 8.29e9 * (BATCH / 256) / (k_ms * 1e-3) / 1e12 / 74.46,
-                         "note": "latency / lock-step bound: FP32 pipe 47 %, issue 44 %, shared-memory pipe 70 % busy under ncu (DESIGN.md 4.1); not HBM bound"},
+                         "note": "FP32-issue / latency bound (12 warps per SM at 168 registers), not HBM bound: see DESIGN.md 4.1 and profiles/stft_mel_summary.json"},
             "clocks": clocks,
         }
         if dp is not None:
