@@ -1038,7 +1038,7 @@ static int v2_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int 
 // m_lo are numbered in bin order (only the non-empty ones: a filter whose run is empty points at a permanent zero slot).
 static int v3_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int n_mels) {
   p->v3_mel_ok = false;
-  if (F != 1025 || n_mels < 1 || n_mels > 128) return AA_OK;   // the kernel keeps 4 filters per lane
+  if (F != 1025 || n_mels < 1 || n_mels + 2 > kV3Runs) return AA_OK;
   std::vector<int> run(F);
   std::vector<float2> w(F, make_float2(0.f, 0.f));
   int prev = -1;
@@ -1071,21 +1071,21 @@ static int v3_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int 
   }
   if (c + 1 > kV3Runs - 1) return AA_OK;
   std::vector<unsigned char> tab(kV3MelTab + 4 * (size_t)n_mels, 0);
-  float4* tw = reinterpret_cast<float4*>(tab.data());
-  uint32_t* masks = reinterpret_cast<uint32_t*>(tab.data() + 32 * 512);
-  uint32_t* first = reinterpret_cast<uint32_t*>(tab.data() + 32 * 512 + 128);
+  float2* tw = reinterpret_cast<float2*>(tab.data());
+  uint32_t* masks = reinterpret_cast<uint32_t*>(tab.data() + 32 * 256);
+  uint32_t* first = reinterpret_cast<uint32_t*>(tab.data() + 32 * 256 + 128);
   for (int g = 0; g < 32; ++g) {
     uint32_t mk = 0;
     for (int t = 0; t < 32; ++t) {
       const int k = 32 * g + t;
-      tw[t * 32 + g] = make_float4(w[k].x, w[k].y, (t == 0 || run[k] != run[k - 1]) ? 0.f : 1.f, 0.f);   // keep = 0: first bin of a run
+      tw[t * 32 + g] = w[k];
       if (run[k + 1] != run[k]) mk |= 1u << t;
     }
     masks[g] = mk;
     first[g] = (uint32_t)slot[32 * g];
     if (g >= 1 && g <= 30 && mk == 0) return AA_OK;   // a segment without a run end: tail targets would collide
   }
-  *reinterpret_cast<float2*>(tab.data() + 32 * 512 + 256) = w[1024];
+  *reinterpret_cast<float2*>(tab.data() + 32 * 256 + 256) = w[1024];
   uint32_t* filt = reinterpret_cast<uint32_t*>(tab.data() + kV3MelTab);
   for (int m = 0; m < n_mels; ++m) filt[m] = (uint32_t)slot_of_run[m + 1] | ((uint32_t)slot_of_run[m] << 16);
   AA_CUDA(cudaMalloc(&p->d_v3_tab, tab.size()));
@@ -1376,8 +1376,6 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
     b.wav_ok16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0 && (n_in & 3) == 0 && (p->hop & 3) == 0) ? 1 : 0;
     static const int v3_prefetch = getenv("AA_STFT_PREFETCH") ? atoi(getenv("AA_STFT_PREFETCH")) : 1;
     b.prefetch = v3_prefetch;
-    static const int v3_diag = getenv("AA_STFT_DIAG") ? atoi(getenv("AA_STFT_DIAG")) : 0;
-    b.diag = v3_diag;
     b.tw1 = p->d_tw1; b.lane_consts = p->d_lane_consts; b.mel_tab = p->d_v3_tab;
     const int smem = v3_smem_bytes(mode, p->n_mels);
     const int64_t tiles = (ni + kV3W - 1) / kV3W;

@@ -23,22 +23,18 @@
 //     (MelScale returns matmul(spec^T, fb)^T, a transposed view).
 #pragma once
 
-#ifndef AA_V3_SHFL
-#define AA_V3_SHFL 0   // partner exchange of the even/odd split by warp shuffles instead of a shared-memory round trip
-#endif
-
 constexpr int kV3W = 12;                 // warps per CTA
 constexpr int kV3Xb = 8456;              // per-warp buffer: 1057 float2
 constexpr int kV3Runs = 136;             // slots of the per-warp run arrays (n_mels + 1 runs at most, last slot = permanent zero)
 constexpr int kV3Tables = 32 * 256 + 512 + 256;   // tw1 [32][32] float2, Hann phases float4[32], W_2048^lane float2[32]
-constexpr int kV3MelTab = 32 * 512 + 32 * 4 + 32 * 4 + 16;   // [32 steps][32 lanes] float4 (w_lo, w_hi, keep, 0), close masks, first run per lane, w(bin 1024)
+constexpr int kV3MelTab = 32 * 256 + 32 * 4 + 32 * 4 + 16;   // weights [32][32] float2, flush masks, first run per lane, w(bin 1024)
 
 struct Stft3Args {
   const float* wav;          // [rows][n_in]
   float* out;
   int rows, n_in, n_pad, n_frames, hop, center_off;
   int n_items;               // row pairs x frames
-  int n_freq, n_mels, wav_ok8, wav_ok16, prefetch, diag;   // diag: timing experiments only (wrong results)
+  int n_freq, n_mels, wav_ok8, wav_ok16, prefetch;
   const float2* tw1;         // [32][32] W_1024^(k1 n2)
   const float* lane_consts;  // float4[32] Hann phases + float2[32] W_2048^lane
   const unsigned char* mel_tab;   // kV3MelTab bytes (see above), then uint32 [n_mels]: run slot of L | run slot of H << 16
@@ -64,49 +60,35 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ void v3_mel_walk(const Stft3Args& a, unsigned char* xb_raw, const unsigned char* s_mel, float4* s_runs,
                                             int lane, long long rowA, int frame, bool hasB) {
   // ---- the warp's own banded mel walk: lane g = bins 32 g .. 32 g + 31
-  uint32_t filt[4];   // run slots of the filters lane + 32 q, needed at the very end: requested first (n_mels <= 128: host check)
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int m = lane + 32 * q;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(filt[q]) : "r"(smem_u32(s_mel + kV3MelTab) + 4u * (uint32_t)(m < a.n_mels ? m : 0)));
-    if (m >= a.n_mels) filt[q] = (uint32_t)(kV3Runs - 1) * 0x10001u;
-  }
   const uint32_t runs = smem_u32(s_runs);
-  const uint32_t wbase = smem_u32(s_mel) + (uint32_t)lane * 16u;
+  const uint32_t wbase = smem_u32(s_mel) + (uint32_t)lane * 8u;
   const uint32_t pbase = smem_u32(xb_raw) + (uint32_t)lane * (33u * 8u);
-  const uint32_t mask = reinterpret_cast<const uint32_t*>(s_mel + 32 * 512)[lane];
-  const uint32_t mp0 = runs + reinterpret_cast<const uint32_t*>(s_mel + 32 * 512 + 128)[lane] * 16u;
-  // One step = one bin: (L, H) = (L, H) * keep + P * (w_lo, w_hi) with keep = 0 on the first bin of a run (1 otherwise; it rides
-  // in the weight table), so nothing is ever cleared and the only dependent chain is one packed FMA per step and sum; a bin that
-  // closes a run stores (L, H) of both rows with one 128-bit store.  The power values and weights of 16 bins are loaded up front
-  // (the FFT registers are free here), so no shared-memory latency sits between the steps.
-  float2 aL = make_float2(0.f, 0.f), aH = aL;
+  const uint32_t mask = reinterpret_cast<const uint32_t*>(s_mel + 32 * 256)[lane];
+  uint32_t mp = runs + reinterpret_cast<const uint32_t*>(s_mel + 32 * 256 + 128)[lane] * 16u;
+  // One step = one bin: (L, H) += P * (w_lo, w_hi); a bin that closes a run stores (L, H) of both rows with one 128-bit store,
+  // advances the run pointer and clears the sums (64-bit clears).
+  unsigned long long aL = 0ull, aH = 0ull;   // packed (rowA, rowB) fp32 pairs
 #pragma unroll
-  for (int h = 0; h < ((a.diag & 16) ? 0 : 2); ++h) {
-    float2 Pv[16];
-    float4 wv[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      Pv[j] = lds_f2(pbase + (uint32_t)(16 * h + j) * 8u);
-      wv[j] = lds_f4(wbase + (uint32_t)(16 * h + j) * 512u);
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int t = 16 * h + j;
-      aL = pfma(aL, wv[j].z, pmuls(Pv[j], wv[j].x));
-      aH = pfma(aH, wv[j].z, pmuls(Pv[j], wv[j].y));
-      if (mask & (1u << t)) {   // slot = first slot of the lane + number of runs closed so far (an independent address per step)
-        const uint32_t sa = mp0 + 16u * (uint32_t)__popc(mask & ((1u << t) - 1u));
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sa), "f"(aL.x), "f"(aL.y), "f"(aH.x), "f"(aH.y) : "memory");
-      }
+  for (int t = 0; t < 32; ++t) {
+    const float2 P = lds_f2(pbase + (uint32_t)t * 8u);
+    const float2 w = lds_f2(wbase + (uint32_t)t * 256u);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(aL) : "l"(*reinterpret_cast<const unsigned long long*>(&P)), "l"(pack2(w.x, w.x)));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(aH) : "l"(*reinterpret_cast<const unsigned long long*>(&P)), "l"(pack2(w.y, w.y)));
+    if (mask & (1u << t)) {
+      asm volatile("st.shared.b64 [%0], %1;" ::"r"(mp), "l"(aL) : "memory");
+      asm volatile("st.shared.b64 [%0+8], %1;" ::"r"(mp), "l"(aH) : "memory");
+      mp += 16u;
+      aL = 0ull;
+      aH = 0ull;
     }
   }
-  const float2 aLf = aL, aHf = aH;
-  const uint32_t mp = mp0 + 16u * (uint32_t)__popc(mask);
+  float2 aLf, aHf;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(aLf.x), "=f"(aLf.y) : "l"(aL));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(aHf.x), "=f"(aHf.y) : "l"(aH));
   const bool open_tail = (mask >> 31) == 0;   // my last bin did not close its run
   if (lane == 31) {   // bin 1024 closes the last run
     const float2 P = lds_f2(smem_u32(xb_raw) + 1056u * 8u);
-    const float2 w = *reinterpret_cast<const float2*>(s_mel + 32 * 512 + 256);
+    const float2 w = *reinterpret_cast<const float2*>(s_mel + 32 * 256 + 256);
     const float2 fL = open_tail ? pfma(P, w.x, aLf) : pmuls(P, w.x), fH = open_tail ? pfma(P, w.y, aHf) : pmuls(P, w.y);
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(mp), "f"(fL.x), "f"(fL.y), "f"(fH.x), "f"(fH.y) : "memory");
   }
@@ -117,18 +99,15 @@ __device__ __forceinline__ void v3_mel_walk(const Stft3Args& a, unsigned char* x
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(mp), "f"(nL.x), "f"(nL.y), "f"(nH.x), "f"(nH.y) : "memory");
   }
   __syncwarp();
+  const uint32_t* s_filt = reinterpret_cast<const uint32_t*>(s_mel + kV3MelTab);
   float* oA = a.out + ((size_t)rowA * (size_t)a.n_frames + (size_t)frame) * (size_t)a.n_mels;
   float* oB = oA + (size_t)a.n_frames * (size_t)a.n_mels;
-  float2 v[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)   // filter lane + 32 q: L of run m + 1 plus H of run m (missing filters point at the zero slot)
-    v[q] = padd(lds_f2(runs + (filt[q] & 0xffffu) * 16u), lds_f2(runs + (filt[q] >> 16) * 16u + 8u));
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    if (lane + 32 * q < a.n_mels) {
-      oA[lane + 32 * q] = v[q].x;
-      if (hasB) oB[lane + 32 * q] = v[q].y;
-    }
+  for (int m = lane; m < a.n_mels; m += 32) {
+    const uint32_t f = s_filt[m];
+    const float2 v = padd(lds_f2(runs + (f & 0xffffu) * 16u), lds_f2(runs + (f >> 16) * 16u + 8u));
+    oA[m] = v.x;
+    if (hasB) oB[m] = v.y;
+  }
   __syncwarp();   // run arrays and P line are consumed before the buffer is reused
 }
 
@@ -193,15 +172,17 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_
         const float2* FB = reinterpret_cast<const float2*>(pa + a.n_in + sf);
         float2 xa[32], xb[32];
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) xa[n1] = __ldg(FA + 32 * n1 + lane);
+        for (int sl = 0; sl < 32; ++sl) {   // in the order the first butterflies consume them (FFT slot order), rows interleaved
+          xa[bitrev5(sl)] = __ldg(FA + 32 * bitrev5(sl) + lane);
+          xb[bitrev5(sl)] = __ldg(FB + 32 * bitrev5(sl) + lane);
+        }
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) xb[n1] = __ldg(FB + 32 * n1 + lane);
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
+        for (int sl = 0; sl < 32; ++sl) {
+          const int n1 = bitrev5(sl);
           const float w0 = fmaf(0.5f * aa_consts::kSin32[n1], ph.y, fmaf(-0.5f * aa_consts::kCos32[n1], ph.x, 0.5f));
           const float w1 = fmaf(0.5f * aa_consts::kSin32[n1], ph.w, fmaf(-0.5f * aa_consts::kCos32[n1], ph.z, 0.5f));
-          re[bitrev5(n1)] = make_float2(xa[n1].x * w0, xb[n1].x * w0);
-          im[bitrev5(n1)] = make_float2(xa[n1].y * w1, xb[n1].y * w1);
+          re[sl] = make_float2(xa[n1].x * w0, xb[n1].x * w0);
+          im[sl] = make_float2(xa[n1].y * w1, xb[n1].y * w1);
         }
       } else {
         // chunk edge / odd last row / unaligned rows: gather the frame with the reference's reflect + zero-pad index math,
@@ -237,7 +218,7 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_
     fft32_dit(re, im);
 #pragma unroll
     for (int j = 1; j < 32; ++j) {
-      const float2 tw = s_tw1[((a.diag & 1) ? 1 : j) * 32 + lane];
+      const float2 tw = s_tw1[j * 32 + lane];
       const float2 r = re[j], i = im[j];
       re[j] = pfma(i, -tw.y, pmuls(r, tw.x));
       im[j] = pfma(i, tw.x, pmuls(r, tw.y));
@@ -256,14 +237,12 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_
     __syncwarp();
     fft32_dit(re, im);   // slot k2 of lane k1: Z[k1 + 32 k2]
     // publish the upper half (k2 >= 16) for the partner lane
-#if !AA_V3_SHFL
 #pragma unroll
     for (int k2 = 16; k2 < 32; ++k2)
       asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(xb4 + (uint32_t)((k2 - 16) * 32 + lane) * 16u), "f"(re[k2].x),
                    "f"(re[k2].y), "f"(im[k2].x), "f"(im[k2].y)
                    : "memory");
     __syncwarp();
-#endif
 
     // Even/odd split for the pair (k, 1024-k), k = lane + 32 i (i < 16): own Z[k] in slot i, partner's Z[1024-k] in lane
     // (32-lane)&31 slot 31-i (lane 0: slot 32-i).  E2 = a + conj(b), O2 = (a - conj(b))/i, T = W_2048^k O2:
@@ -274,18 +253,9 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_
       float2 pk[16], pq[16];   // 4|X[k]|^2, 4|X[1024-k]|^2
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-#if AA_V3_SHFL
-        float4 bq;   // partner lane's slot 31 - i, straight from its registers (lane 0: own slot 32 - i)
-        bq.x = __shfl_sync(0xffffffffu, re[31 - i].x, plane);
-        bq.y = __shfl_sync(0xffffffffu, re[31 - i].y, plane);
-        bq.z = __shfl_sync(0xffffffffu, im[31 - i].x, plane);
-        bq.w = __shfl_sync(0xffffffffu, im[31 - i].y, plane);
-        if (i > 0 && lane == 0) bq = make_float4(re[i > 0 ? 32 - i : 31].x, re[i > 0 ? 32 - i : 31].y, im[i > 0 ? 32 - i : 31].x, im[i > 0 ? 32 - i : 31].y);
-#else
         int ps = pshift - i;
         ps = ps > 15 ? 15 : ps;
         const float4 bq = lds_f4(xb4 + (uint32_t)(ps * 32 + plane) * 16u);
-#endif
         const float2 br = make_float2(bq.x, bq.y), bi = make_float2(bq.z, bq.w);
         const float2 ar = re[i], ai = im[i];
         const float2 tw = make_float2(fmaf(cl.y, aa_consts::kSin64[i], cl.x * aa_consts::kCos64[i]),
@@ -314,25 +284,16 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft2048_v3_kernel(const __grid_
       }
       if (lane == 0) sts_f2(smem_u32(xb_raw) + 528u * 8u, pmuls(pfma2(z16i, z16i, pmul(z16r, z16r)), 4.f));   // bin 512
       __syncwarp();
-      if (!(a.diag & 4)) v3_mel_walk(a, xb_raw, s_mel, s_runs, lane, rowA, frame, hasB);
+      v3_mel_walk(a, xb_raw, s_mel, s_runs, lane, rowA, frame, hasB);
     } else {
       // complex / power, frequency-minor output [row][frame][1025]: stored straight from registers
       const long long e0 = (rowA * (long long)a.n_frames + frame) * a.n_freq;
       const long long e1 = e0 + (long long)a.n_frames * a.n_freq;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-#if AA_V3_SHFL
-        float4 bq;   // partner lane's slot 31 - i, straight from its registers (lane 0: own slot 32 - i)
-        bq.x = __shfl_sync(0xffffffffu, re[31 - i].x, plane);
-        bq.y = __shfl_sync(0xffffffffu, re[31 - i].y, plane);
-        bq.z = __shfl_sync(0xffffffffu, im[31 - i].x, plane);
-        bq.w = __shfl_sync(0xffffffffu, im[31 - i].y, plane);
-        if (i > 0 && lane == 0) bq = make_float4(re[i > 0 ? 32 - i : 31].x, re[i > 0 ? 32 - i : 31].y, im[i > 0 ? 32 - i : 31].x, im[i > 0 ? 32 - i : 31].y);
-#else
         int ps = pshift - i;
         ps = ps > 15 ? 15 : ps;
         const float4 bq = lds_f4(xb4 + (uint32_t)(ps * 32 + plane) * 16u);
-#endif
         const float2 br = make_float2(bq.x, bq.y), bi = make_float2(bq.z, bq.w);
         const float2 ar = re[i], ai = im[i];
         const float2 tw = make_float2(fmaf(cl.y, aa_consts::kSin64[i], cl.x * aa_consts::kCos64[i]),
