@@ -922,7 +922,10 @@ struct AaStftPlan {
   int4* d_v2_groups = nullptr;   // warp start indices + 48-byte group records of the banded mel walk
   int v2_groups_len = 0;
   // stft2048_v3_kernel (no inter-warp synchronisation; warp-private mel walk, [row][frame][mel] output)
+  bool v3 = false;                     // n_fft = 2048 / 1024, periodic Hann window, even hop: stft_v3_kernel can run the plan
   bool v3_mel_ok = false;
+  float2* d_v3_tw1 = nullptr;          // [32 / FR][32] W_(n_fft/2)^(k1 n2)
+  float* d_v3_lane = nullptr;          // float4[32] Hann phases + float2[32] W_n_fft^(k1 of the lane)
   unsigned char* d_v3_tab = nullptr;   // kV3MelTab bytes + uint32 [n_mels] run slots (see stft2048_v3.cuh)
   // resources of aa_stft_mel_f32_host (created lazily)
   cudaStream_t hstream[2] = {nullptr, nullptr};
@@ -1038,7 +1041,8 @@ static int v2_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int 
 // m_lo are numbered in bin order (only the non-empty ones: a filter whose run is empty points at a permanent zero slot).
 static int v3_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int n_mels) {
   p->v3_mel_ok = false;
-  if (F != 1025 || n_mels < 1 || n_mels + 2 > kV3Runs) return AA_OK;
+  if (!p->v3 || (F != 1025 && F != 513) || n_mels < 1 || n_mels + 2 > kV3Runs) return AA_OK;
+  const int segs = (F - 1) / 32;       // 32-bin segments per frame: 32 (n_fft = 2048) or 16 (n_fft = 1024: lanes 16..31 = second frame)
   std::vector<int> run(F);
   std::vector<float2> w(F, make_float2(0.f, 0.f));
   int prev = -1;
@@ -1075,17 +1079,18 @@ static int v3_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int 
   uint32_t* masks = reinterpret_cast<uint32_t*>(tab.data() + 32 * 256);
   uint32_t* first = reinterpret_cast<uint32_t*>(tab.data() + 32 * 256 + 128);
   for (int g = 0; g < 32; ++g) {
+    const int fr = g / segs, sg = g % segs;
     uint32_t mk = 0;
     for (int t = 0; t < 32; ++t) {
-      const int k = 32 * g + t;
+      const int k = 32 * sg + t;
       tw[t * 32 + g] = w[k];
       if (run[k + 1] != run[k]) mk |= 1u << t;
     }
     masks[g] = mk;
-    first[g] = (uint32_t)slot[32 * g];
-    if (g >= 1 && g <= 30 && mk == 0) return AA_OK;   // a segment without a run end: tail targets would collide
+    first[g] = (uint32_t)(fr * kV3Runs + slot[32 * sg]);
+    if (sg >= 1 && sg <= segs - 2 && mk == 0) return AA_OK;   // a segment without a run end: tail targets would collide
   }
-  *reinterpret_cast<float2*>(tab.data() + 32 * 256 + 256) = w[1024];
+  *reinterpret_cast<float2*>(tab.data() + 32 * 256 + 256) = w[F - 1];
   uint32_t* filt = reinterpret_cast<uint32_t*>(tab.data() + kV3MelTab);
   for (int m = 0; m < n_mels; ++m) filt[m] = (uint32_t)slot_of_run[m + 1] | ((uint32_t)slot_of_run[m] << 16);
   AA_CUDA(cudaMalloc(&p->d_v3_tab, tab.size()));
@@ -1094,8 +1099,36 @@ static int v3_build_mel(AaStftPlan* p, const std::vector<float>& fb, int F, int 
   return AA_OK;
 }
 
-static int v3_smem_bytes(int mode, int n_mels) {
-  const int mel_bytes = mode == MODE_MEL ? ((kV3MelTab + 4 * n_mels + 15) & ~15) + kV3W * kV3Runs * 16 : 0;
+// twiddle / window tables of stft_v3_kernel for n_fft = 2048 / 1024
+static int v3_build_tables(AaStftPlan* p) {
+  const double PI = 3.14159265358979323846;
+  const int nf = p->n_fft, fr = 2048 / nf, r1 = 32 / fr, h = nf / 2;
+  std::vector<float2> tw((size_t)r1 * 32);
+  for (int k1 = 0; k1 < r1; ++k1)
+    for (int n2 = 0; n2 < 32; ++n2) {
+      const double th = -2.0 * PI * (double)(k1 * n2) / (double)h;
+      tw[(size_t)k1 * 32 + n2] = make_float2((float)std::cos(th), (float)std::sin(th));
+    }
+  std::vector<float> lc(32 * 4 + 32 * 2);
+  for (int l = 0; l < 32; ++l) {
+    for (int e = 0; e < 2; ++e) {
+      const double phi = 2.0 * PI * (double)(2 * l + e) / (double)nf;
+      lc[4 * l + 2 * e] = (float)std::cos(phi);
+      lc[4 * l + 2 * e + 1] = (float)std::sin(phi);
+    }
+    const int k1 = l % r1;
+    lc[128 + 2 * l] = (float)std::cos(2.0 * PI * k1 / (double)nf);
+    lc[128 + 2 * l + 1] = (float)(-std::sin(2.0 * PI * k1 / (double)nf));
+  }
+  AA_CUDA(cudaMalloc(&p->d_v3_tw1, sizeof(float2) * tw.size()));
+  AA_CUDA(cudaMemcpy(p->d_v3_tw1, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+  AA_CUDA(cudaMalloc(&p->d_v3_lane, sizeof(float) * lc.size()));
+  AA_CUDA(cudaMemcpy(p->d_v3_lane, lc.data(), sizeof(float) * lc.size(), cudaMemcpyHostToDevice));
+  return AA_OK;
+}
+
+static int v3_smem_bytes(int mode, int n_mels, int n_fft) {
+  const int mel_bytes = mode == MODE_MEL ? ((kV3MelTab + 4 * n_mels + 15) & ~15) + kV3W * (2048 / n_fft) * kV3Runs * 16 : 0;
   return kV3W * kV3Xb + kV3Tables + mel_bytes + 16;
 }
 
@@ -1130,6 +1163,11 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
   for (int i = 0; i < n_fft; ++i)
     if (std::fabs(win[i] - (float)(0.5 - 0.5 * std::cos(2.0 * PI * i / n_fft))) > 2e-6f) { is_hann = false; break; }
   p->fast = (n_fft == 2048) && (hop % 4 == 0) && (hop <= 1024) && is_hann;
+  p->v3 = (n_fft == 2048 || n_fft == 1024) && (hop % 2 == 0) && is_hann;
+  if (p->v3) {
+    rc = v3_build_tables(p);
+    if (rc != AA_OK) return rc;
+  }
   AA_CUDA(cudaMalloc(&p->d_window2, sizeof(float) * n_fft));
   AA_CUDA(cudaMemcpy(p->d_window2, win.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
   // twiddles
@@ -1225,6 +1263,8 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
     p->mel_w4_count = (int)(w.size() / 4);
     AA_CUDA(cudaMalloc(&p->d_mel_w4, sizeof(float) * w.size()));
     AA_CUDA(cudaMemcpy(p->d_mel_w4, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+    rc = v3_build_mel(p, fb, F, n_mels);
+    if (rc != AA_OK) return rc;
     if (p->fast) {
       // Step lists of the fused mel epilogue.  A step = 4 adjacent filters; its weight block is
       // [n_iter][4 filters] float4 (4 bins each), n_iter = the longest filter of the step, shorter filters
@@ -1286,8 +1326,6 @@ int aa_stft_plan_create(AaStftPlan** plan_out, int n_fft, int hop, int center, c
                          cudaMemcpyHostToDevice));
       rc = v2_build_mel(p, fb, F, n_mels);
       if (rc != AA_OK) return rc;
-      rc = v3_build_mel(p, fb, F, n_mels);
-      if (rc != AA_OK) return rc;
     }
   }
   if (p->fast) {
@@ -1313,7 +1351,7 @@ int aa_stft_plan_destroy(AaStftPlan* p) {
   if (!p) return AA_OK;
   cudaFree(p->d_window2); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_mel_meta); cudaFree(p->d_mel_w4); cudaFree(p->d_mel_steps); cudaFree(p->d_lane_consts); cudaFree(p->d_wk);
   cudaFree(p->d_v2_groups);
-  cudaFree(p->d_v3_tab);
+  cudaFree(p->d_v3_tab); cudaFree(p->d_v3_tw1); cudaFree(p->d_v3_lane);
   for (int i = 0; i < 2; ++i) {
     if (p->hbuf_in[i]) cudaFree(p->hbuf_in[i]);
     if (p->hbuf_out[i]) cudaFree(p->hbuf_out[i]);
@@ -1363,29 +1401,35 @@ static int stft_launch(const AaStftPlan* p, int mode, const float* wav, int64_t 
   a.wav_aligned16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0) ? 1 : 0;
   const bool big_out = rows * (int64_t)std::max(p->n_freq, p->n_mels) * n_frames >= (1LL << 31);
   const int v3_mode = getenv("AA_STFT_V3") ? atoi(getenv("AA_STFT_V3")) : 1;      // 0: older kernels only
-  AA_REQUIRE(!(mode == MODE_MEL && out_tf) || (p->fast && p->v3_mel_ok && !big_out),
-             "the [row][frame][mel] layout needs n_fft = 2048 with a Hann window and a banded filterbank (aa_stft_mel_tf_supported)");
-  if (p->fast && !big_out && out_tf && (v3_mode || mode == MODE_MEL) && rows < (1LL << 30) && n_pad < (1LL << 30)) {
+  AA_REQUIRE(!(mode == MODE_MEL && out_tf) || (p->v3 && p->v3_mel_ok && !big_out),
+             "the [row][frame][mel] layout needs n_fft = 2048 / 1024 with a Hann window, an even hop and a banded filterbank (aa_stft_mel_tf_supported)");
+  if (p->v3 && !big_out && out_tf && (v3_mode || mode == MODE_MEL) && rows < (1LL << 30) && n_pad < (1LL << 30)) {
+    const int fr = 2048 / p->n_fft;
     Stft3Args b;
     b.wav = wav; b.out = out; b.rows = (int)rows; b.n_in = (int)n_in; b.n_pad = (int)n_pad; b.n_frames = (int)n_frames;
     b.hop = p->hop; b.center_off = a.center_off;
-    const int64_t ni = ((rows + 1) / 2) * n_frames;
+    b.items_per_pair = (int)((n_frames + fr - 1) / fr);
+    const int64_t ni = ((rows + 1) / 2) * b.items_per_pair;
     AA_REQUIRE(ni < (1LL << 31) - 4096 * kV3W, "problem too large for the fast STFT path");
     b.n_items = (int)ni; b.n_freq = p->n_freq; b.n_mels = p->n_mels;
     b.wav_ok8 = ((reinterpret_cast<uintptr_t>(wav) & 7) == 0 && (n_in & 1) == 0 && (p->hop & 1) == 0) ? 1 : 0;
     b.wav_ok16 = ((reinterpret_cast<uintptr_t>(wav) & 15) == 0 && (n_in & 3) == 0 && (p->hop & 3) == 0) ? 1 : 0;
-    static const int v3_prefetch = getenv("AA_STFT_PREFETCH") ? atoi(getenv("AA_STFT_PREFETCH")) : 1;
+    static const int v3_prefetch = getenv("AA_STFT_PREFETCH") ? atoi(getenv("AA_STFT_PREFETCH")) : 0;
     b.prefetch = v3_prefetch;
-    b.tw1 = p->d_tw1; b.lane_consts = p->d_lane_consts; b.mel_tab = p->d_v3_tab;
-    const int smem = v3_smem_bytes(mode, p->n_mels);
+    b.tw1 = p->d_v3_tw1; b.lane_consts = p->d_v3_lane; b.mel_tab = p->d_v3_tab;
+    const int smem = v3_smem_bytes(mode, p->n_mels, p->n_fft);
     const int64_t tiles = (ni + kV3W - 1) / kV3W;
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)aa::num_sms());
-#define AA_V3(MD)                                                               \
+#define AA_V3(NFFT, MD)                                                         \
   do {                                                                          \
-    AA_CUDA(aa::ensure_dyn_smem(stft2048_v3_kernel<MD>, smem));                 \
-    stft2048_v3_kernel<MD><<<grid, kV3W * 32, smem, st>>>(b);                   \
+    AA_CUDA(aa::ensure_dyn_smem(stft_v3_kernel<NFFT, MD>, smem));               \
+    stft_v3_kernel<NFFT, MD><<<grid, kV3W * 32, smem, st>>>(b);                 \
   } while (0)
-    if (mode == MODE_COMPLEX) AA_V3(MODE_COMPLEX); else if (mode == MODE_POWER) AA_V3(MODE_POWER); else AA_V3(MODE_MEL);
+    if (p->n_fft == 2048) {
+      if (mode == MODE_COMPLEX) AA_V3(2048, MODE_COMPLEX); else if (mode == MODE_POWER) AA_V3(2048, MODE_POWER); else AA_V3(2048, MODE_MEL);
+    } else {
+      if (mode == MODE_COMPLEX) AA_V3(1024, MODE_COMPLEX); else if (mode == MODE_POWER) AA_V3(1024, MODE_POWER); else AA_V3(1024, MODE_MEL);
+    }
 #undef AA_V3
     AA_LAUNCH_CHECK();
     return AA_OK;
@@ -1510,7 +1554,7 @@ int aa_stft_mel_tf_f32(const AaStftPlan* plan, const float* wav, int64_t rows, i
                        float* out, void* stream) {
   return stft_launch(plan, MODE_MEL, wav, rows, n_in, zero_pad, out, (cudaStream_t)stream, 1);
 }
-int aa_stft_mel_tf_supported(const AaStftPlan* plan) { return (plan && plan->fast && plan->v3_mel_ok) ? 1 : 0; }
+int aa_stft_mel_tf_supported(const AaStftPlan* plan) { return (plan && plan->v3 && plan->v3_mel_ok) ? 1 : 0; }
 
 int aa_magdphase_f32(const float* spec, int64_t c, int64_t n_freq, int64_t n_frames, float* out, void* stream) {
   AA_REQUIRE(spec && out, "NULL tensor pointer");

@@ -12,7 +12,7 @@ for name, cls in [("mel", aab.MelSpectrogramAE), ("power", aab.MagSpectrogramAE)
     if name not in os.environ.get("MODES", "mel,power,complex").split(","):
         continue
     kw = dict(sample_rate=48000) if name == "mel" else {}
-    m = cls(n_fft=2048, hop_length=int(os.environ.get("HOP", 512)), center=os.environ.get("CENTER", "1") == "1", **kw)
+    m = cls(n_fft=int(os.environ.get("NFFT", 2048)), hop_length=int(os.environ.get("HOP", 512)), center=os.environ.get("CENTER", "1") == "1", **kw)
     ekw = dict(freq_major=True) if (name == "mel" and os.environ.get("FREQ_MAJOR")) else {}
     for _ in range(3):
         out = m.encode(x, **ekw)
