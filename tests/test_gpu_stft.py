@@ -317,3 +317,30 @@ def test_mel_layout_matches_torchaudio(aab):
     assert mel.encode(x, out=out_c) is out_c and rel_l2(out_c, ref) < TOL
     assert mel.encode(x, out=out_t) is out_t and rel_l2(out_t, ref) < TOL
     assert torch.equal(out_t, yh)
+
+
+@pytest.mark.parametrize("hop,n,rows", [(256, 131072, (2, 2)), (256, 20000, (3, 1)), (128, 16384, (1, 2)), (512, 40000, (2, 2)), (250, 9000, (1, 3)),
+                                        (255, 9000, (1, 2))])
+def test_v3_kernel_n1024_two_frames_per_item(aab, monkeypatch, hop, n, rows):
+    """stft_v3_kernel<1024>: the reference-default transform size, two consecutive frames per warp item.  Against the float64
+    oracle and the older kernels: odd frame counts (the second frame of the last item does not exist), odd row counts, lengths
+    that are not powers of two (zero_pad_po2 tail inside a frame), chunk edges, a hop that is even but not a multiple of 4 and
+    an odd hop (not eligible: warp kernel, contiguous layout)."""
+    from oracle import aa_oracle as O
+    g = torch.Generator().manual_seed(1024 + hop + n)
+    x = torch.rand(*rows, n, generator=g) - 0.5
+    ref = O.mel_spectrogram(x, 48000, 1024, hop)
+    mel = aab.MelSpectrogramAE(sample_rate=48000, n_fft=1024, hop_length=hop)
+    y3 = mel.encode(x.cuda())
+    assert tuple(y3.shape) == tuple(ref.shape) and rel_l2(y3, ref) < 1e-5
+    if hop % 2 == 0:
+        assert y3.stride()[-2:] == (1, 128), "v3 kernel: torchaudio's own layout (a transposed view)"
+    yc = mel.encode(x.cuda(), freq_major=True)            # warp kernel, contiguous [.., mel, T]
+    assert yc.is_contiguous() and rel_l2(yc, y3) < 2e-6
+    refp = O.power_spectrogram(x, 1024, hop)
+    for v3 in ("1", "0"):
+        monkeypatch.setenv("AA_STFT_V3", v3)
+        yp = aab.MagSpectrogramAE(n_fft=1024, hop_length=hop).encode(x.cuda())
+        ycx = aab.SpectrogramAE(n_fft=1024, hop_length=hop).encode(x.cuda())
+        assert rel_l2(yp, refp) < 1e-5, f"power, AA_STFT_V3={v3}"
+        assert rel_l2(ycx.abs() ** 2, yp) < 1e-5
