@@ -9,6 +9,7 @@
 #include "aa_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <cmath>
 
@@ -506,6 +507,11 @@ inline int parts_for(long long n) {
 
 }  // namespace
 
+namespace aa {   // csrc/gram_tc.cu
+int64_t gram_tc_workspace_floats();
+int gram_tc(const float* y, int64_t b, int64_t t, float* cov_num, double* count, float* workspace, cudaStream_t stream);
+}
+
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -681,7 +687,7 @@ static int scatter_blocks() { return 2 * aa::num_sms(); }
 
 int64_t aa_cov_workspace_floats(int64_t c) {
   const int64_t slices = 64;
-  return (int64_t)scatter_blocks() * c * c + c * slices + c + 64;
+  return std::max<int64_t>((int64_t)scatter_blocks() * c * c + c * slices + c + 64, aa::gram_tc_workspace_floats());
 }
 
 int aa_cov_accumulate_f32(const float* y, int64_t b, int64_t c, int64_t t, float* cov_num, double* count, float* workspace,
@@ -689,6 +695,9 @@ int aa_cov_accumulate_f32(const float* y, int64_t b, int64_t c, int64_t t, float
   AA_REQUIRE(y && cov_num && workspace, "NULL argument");
   AA_REQUIRE(b >= 1 && c >= 1 && t >= 1 && c <= 4096, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
+  // 64 channels (every given model's latent width): one pass over the latents, rank-n update on tcgen05 (csrc/gram_tc.cu)
+  if (c == 64 && (t & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && getenv("AA_PCA_CUDA_CORES") == nullptr)
+    return aa::gram_tc(y, b, t, cov_num, count, workspace, st);
   const int slices = 64;
   float* parts = workspace;                                   // [blocks][c][c]
   float* sums = workspace + (int64_t)scatter_blocks() * c * c;  // [c][slices]

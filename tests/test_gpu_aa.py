@@ -351,6 +351,24 @@ def test_pca_accumulation_golden(aab, golden):
     assert rel_l2(rc2.cov_numerator, num) < 1e-5 and int(rc2.count.item()) == n
 
 
+def test_pca_tensor_core_path_matches_oracle_and_cuda_core_path(aab, monkeypatch):
+    """C = 64: one pass, the 64 x 64 rank-n update on tcgen05 (hi / lo TF32 split, csrc/gram_tc.cu).  Against the float64 oracle
+    and the two-pass CUDA-core kernel: a large mean (the pivot keeps the raw moments conditioned), a T that is not a multiple of
+    the 64-point tile, several updates (accumulation), more tiles than CTAs."""
+    O = _oracle()
+    g = torch.Generator().manual_seed(5)
+    for shape, shift in (((3, 64, 512), 0.0), ((5, 64, 100), 3.0), ((300, 64, 128), -0.5), ((1, 64, 4), 0.1)):
+        y = torch.tanh(torch.randn(*shape, generator=g)) + shift
+        num, n = O.pca_cov_numerator(y.double())
+        rc = aab.pca.RunningCovariance(64, "cuda").update(y.cuda()).update(y.cuda())
+        assert int(rc.count.item()) == 2 * n
+        assert rel_l2(rc.cov_numerator, 2 * num) < 1e-5, shape
+        monkeypatch.setenv("AA_PCA_CUDA_CORES", "1")
+        rc1 = aab.pca.RunningCovariance(64, "cuda").update(y.cuda()).update(y.cuda())
+        monkeypatch.delenv("AA_PCA_CUDA_CORES")
+        assert rel_l2(rc.cov_numerator, rc1.cov_numerator) < 1e-5
+
+
 def test_adam_matches_torch(aab):
     from audio_algebra_b200.training import FlatAdam
     O = _oracle()
