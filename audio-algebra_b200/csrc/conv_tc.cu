@@ -48,6 +48,7 @@ struct TcArgs {
   float* out_f32;                   // [B][cout][lout] fp32 channel-major (last layer), or NULL
   long long out_row_stride;         // rows per batch element in `out` / `res`
   int elu, tanh_out;
+  int res_tma;                      // RES layers with bn % 64 == 0: residual tile in / result tile out through TMA (see the epilogue)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +85,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+// shared -> global tile store (bulk async group of the issuing thread); rows / columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -149,7 +156,9 @@ __device__ __forceinline__ float elu1(float v) { return fmaxf(v, 0.f) + (__expf(
 // RES: the layer adds a residual (ROLE_RES_SECOND); compile-time so that the epilogue carries no per-element branches
 template <int BK, bool RES>
 __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmR,
+                                                                const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
   constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -161,6 +170,12 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
   auto tempty_bar = [&](int i) { return bars + 8u * (2 * a.stages + kMaxAcc + i); };
   const uint32_t tmem_slot = bars + 8u * (2 * a.stages + 2 * kMaxAcc);
+  // res_tma: per epilogue group one [bn / 64][128 rows][128 B] SWIZZLE_128B tile buffer (residual in, result out, in place) at
+  // bars + 1024 + g * (BM * bn * 2 + 1024), followed by the group's bias copy; rfull[g] = residual landed, rempty[g] = the
+  // group's previous result has been read out of the buffer by its TMA store
+  auto rfull_bar = [&](int g) { return bars + 384u + 8u * g; };
+  auto rempty_bar = [&](int g) { return bars + 416u + 8u * g; };
+  const uint32_t RBUF = (uint32_t)BM * (uint32_t)a.bn * 2u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int acc_cols = a.n_acc * a.bn;
   const uint32_t tmem_cols = (acc_cols <= 32) ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
@@ -168,9 +183,14 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int i = 0; i < a.n_acc; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    for (int g = 0; g < kMaxEpi; ++g) { mbar_init(rfull_bar(g), 1); mbar_init(rempty_bar(g), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (RES && a.res_tma) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    }
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
@@ -192,7 +212,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
       const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
       int s = 0;
       uint32_t ph = 0;
-      for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+      int it = 0;
+      for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int b = (int)(t / tiles_per_b);
         const int r = (int)(t % tiles_per_b);
         const int nt = r % a.n_tiles_n, mt = r / a.n_tiles_n;
@@ -207,6 +228,18 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
             tma_load_2d(sa + A_BYTES, &tmB, fb, q * BK, n0);
           }
           if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+        if (RES && a.res_tma) {
+          // this tile's residual -> its epilogue group's buffer: ONE DRAM round trip, requested before the tile's MMAs have run.
+          // (Measured alternative: the group's leader thread requesting the group's next residual right after its store --
+          // no coupling to this warp -- was slower at C = 128: 78 vs 67 us.)
+          const int g = it % a.n_epi, k = it / a.n_epi;
+          if (k > 0) mbar_wait(ubars + 416u + 8u * g, (uint32_t)(k - 1) & 1u);
+          const uint32_t rb = ubars + 1024u + (uint32_t)g * (RBUF + 1024u), rf = ubars + 384u + 8u * g;
+          if (elect_one()) {
+            mbar_expect_tx(rf, RBUF);
+            for (int bx = 0; bx < a.bn / 64; ++bx) tma_load_3d(rb + (uint32_t)bx * 16384u, &tmR, rf, n0 + 64 * bx, m0, b);
+          }
         }
       }
     }
@@ -249,10 +282,12 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
     const int et = (threadIdx.x - 64) & 127;               // 0..127 within the group
     const uint32_t RS = (uint32_t)a.bn * 2u + 16u;         // row stride in bytes
     const uint32_t grp_bytes = (a.out_f32 == nullptr ? (uint32_t)BM * RS : 0u) + (uint32_t)a.bn * 4u;
-    const uint32_t stg = bars + 512u + (uint32_t)grp * grp_bytes;   // this group's staging area, then its bias copy
+    const bool rtma = RES && a.res_tma != 0;
+    const uint32_t stg = rtma ? bars + 1024u + (uint32_t)grp * (RBUF + 1024u)
+                              : bars + 512u + (uint32_t)grp * grp_bytes;   // this group's staging area, then its bias copy
     const int vec_per_row = a.bn / 8;                      // 16-byte vectors per row (power of two)
     const int vpr_shift = 31 - __clz(vec_per_row);
-    const uint32_t sbias = stg + (a.out_f32 == nullptr ? (uint32_t)BM * RS : 0u);   // bn floats
+    const uint32_t sbias = rtma ? stg + RBUF : stg + (a.out_f32 == nullptr ? (uint32_t)BM * RS : 0u);   // bn floats
     const int bar_id = 1 + grp;
     int bias_n0 = -1;
     int it = 0;
@@ -275,7 +310,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         bias_n0 = n0;
       }
-      if (RES && a.out_f32 == nullptr) {                    // residual tile -> staging (overlaps with the MMAs)
+      if (RES && a.out_f32 == nullptr && !rtma) {           // residual tile -> staging (overlaps with the MMAs)
         // loads in batches of 4 before their shared-memory stores: one L2 round trip per batch, not per 16-byte piece
         const int n_vec = BM * vec_per_row;                 // multiple of 512 (bn >= 32)
         const __nv_bfloat16* rbase = a.res + tile_off;
@@ -302,6 +337,55 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
       mbar_wait(tfull_bar(acc), ((uint32_t)(it / a.n_acc)) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
+      if (rtma) {
+        // The residual tile was laid down by TMA (SWIZZLE_128B: 128-byte rows of 64 channels, 16-byte piece p of row r at
+        // ((p ^ (r & 7)) << 4) -- conflict free for lanes = consecutive rows); the result overwrites it IN PLACE (a thread touches
+        // only its own row's pieces) and leaves through ONE TMA store per 64-channel box: no per-thread global loads (their four
+        // dependent DRAM round trips per tile were the critical path of the 1x1 layers: ncu long_scoreboard 3.3 cycles per issued
+        // instruction at 58 % of the HBM roofline), no copy-out loop.
+        mbar_wait(rfull_bar(grp), ((uint32_t)(it / a.n_epi)) & 1u);
+        const uint32_t rrow = stg + (uint32_t)row_in_tile * 128u;
+        const uint32_t rx = (uint32_t)(row_in_tile & 7);
+        for (int c0 = 0; c0 < a.bn; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          float bia[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bia[j]), "=f"(bia[j + 1]), "=f"(bia[j + 2]), "=f"(bia[j + 3])
+                         : "r"(sbias + 4u * (uint32_t)(c0 + j)));
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t col = (uint32_t)c0 + 8u * g;
+            const uint32_t addr = rrow + (col >> 6) * 16384u + ((((col & 63u) >> 3) ^ rx) << 4);
+            float2 y0 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(bia[8 * g + 0], bia[8 * g + 1]));
+            float2 y1 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(bia[8 * g + 2], bia[8 * g + 3]));
+            float2 y2 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bia[8 * g + 4], bia[8 * g + 5]));
+            float2 y3 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bia[8 * g + 6], bia[8 * g + 7]));
+            uint4 rres;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres.x), "=r"(rres.y), "=r"(rres.z), "=r"(rres.w) : "r"(addr));
+            y0 = __fadd2_rn(y0, unpack_bf16(rres.x));
+            y1 = __fadd2_rn(y1, unpack_bf16(rres.y));
+            y2 = __fadd2_rn(y2, unpack_bf16(rres.z));
+            y3 = __fadd2_rn(y3, unpack_bf16(rres.w));
+            uint4 o = make_uint4(pack_bf16(elu2(y0)), pack_bf16(elu2(y1)), pack_bf16(elu2(y2)), pack_bf16(elu2(y3)));
+            if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+        }
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is read by the TMA store (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));          // accumulator drained: the MMA warp may reuse it
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // tile complete in the buffer
+        if (et == 0) {
+          for (int bx = 0; bx < a.bn / 64; ++bx) tma_store_3d(&tmO, stg + (uint32_t)bx * 16384u, n0 + 64 * bx, m0, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has read the buffer: the next residual may land
+          mbar_arrive(rempty_bar(grp));
+        }
+        continue;
+      }
       for (int c0 = 0; c0 < a.bn; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);   // warp-collective: every lane participates
@@ -365,6 +449,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // staging free for the next tile
       }
     }
+    if (rtma && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's tile stores are complete
   }
 
   tc_fence_before();
@@ -727,6 +812,8 @@ struct TcState {
   bool fuse_ru = true;          // ResidualUnits with C = 32 / 64 / 128 run as one fused kernel (conv_ru.cuh)
   bool fuse_ru128 = false;
   int ru_ctas_per_sm[2] = {1, 1};
+  int bn_1x1_wide = 0;
+  int res_tma = 1;             // ResidualUnit 1x1 layers: residual / result tiles through TMA (AA_RES_TMA=0: per-thread loads, staged stores)
 };
 
 static int plan_layer(const ConvLayer& l, LayerPlan& p, bool tf32 = false) {
@@ -792,6 +879,8 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   // the C = 32 kernel is sized for two CTAs per SM (105 KB shared memory, 80 registers x 320 threads, 128 TMEM columns each);
   // the persistent tile loop is correct for any grid, so a conservative occupancy answer only costs a second wave
   st->ru_ctas_per_sm[0] = std::max(st->ru_ctas_per_sm[0], getenv("AA_RU_CTAS32") ? atoi(getenv("AA_RU_CTAS32")) : 2);
+  if (getenv("AA_RES_TMA")) st->res_tma = atoi(getenv("AA_RES_TMA"));
+  if (getenv("AA_1X1_BN256")) st->bn_1x1_wide = atoi(getenv("AA_1X1_BN256"));
   if (getenv("AA_DEBUG")) fprintf(stderr, "[aa] ru_fused CTAs/SM: C=32 -> %d, C=64 -> %d\n", st->ru_ctas_per_sm[0], st->ru_ctas_per_sm[1]);
   *out = st;
   return AA_OK;
@@ -937,7 +1026,11 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     }
     const int n_chunks_total = p.k_total / p.bk;
     // K-light layers (1x1 convs) are epilogue bound: narrower N tiles and more epilogue groups in flight
-    const int bn = std::min(ly.cout, (n_chunks_total <= 8 && !last) ? 128 : 256);
+    int bn = std::min(ly.cout, (n_chunks_total <= 8 && !last) ? 128 : 256);
+    // 8-chunk layers without a residual (the 128 -> 256 down-conv): one 256-wide tile reads the activations once: 97 -> 86 us.
+    // (The C = 512 1x1 layers measured 113 us at bn = 128, 110 us at bn = 256 with res_tma, 147 us at bn = 256 without: unchanged
+    //  unless the dev knob AA_1X1_BN256=1 is set.)
+    if (n_chunks_total == 8 && !last && ly.cout >= 256 && (ly.role != ROLE_RES_SECOND || st->bn_1x1_wide)) bn = 256;
     {
       cuuint64_t dims[2] = {(cuuint64_t)p.k_total, (cuuint64_t)ly.cout};
       cuuint64_t strides[1] = {(cuuint64_t)p.k_total * 2};
@@ -968,20 +1061,37 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     const int stage_bytes = BM * p.bk * 2 + ((bn * p.bk * 2 + 1023) & ~1023);
     a.n_epi = last ? 1 : (bn <= 64 ? 4 : (bn <= 128 ? (n_chunks_total <= 8 ? 3 : 2) : 1));
     a.n_acc = std::min(kMaxAcc, std::min(512 / bn, 2 * a.n_epi));
-    const int staging = a.n_epi * ((last ? 0 : BM * (bn * 2 + 16)) + bn * 4);
+    // ResidualUnit 1x1 layers with 64-channel boxes: residual in / result out through TMA, in place in one swizzled tile buffer per group
+    // (measured per layer at B = 64: C = 128 95 -> 67 us, C = 256 98 -> 79 us; C = 512 -- 8 K chunks, bound by re-streaming the
+    //  weights from L2 for every tile -- 110 -> 120 us: those layers keep the per-thread path unless AA_RES_TMA=2)
+    a.res_tma = (a.res != nullptr && !last && bn % 64 == 0 && (st->res_tma > 1 || (st->res_tma == 1 && n_chunks_total <= 4))) ? 1 : 0;
+    const int staging = a.res_tma ? 512 + a.n_epi * (BM * bn * 2 + 1024) : a.n_epi * ((last ? 0 : BM * (bn * 2 + 16)) + bn * 4);
     a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging) / stage_bytes));
     const int smem = a.stages * stage_bytes + 1024 + 512 + staging;
+    CUtensorMap tmR = tmA, tmO = tmA;   // placeholders unless res_tma
+    if (a.res_tma) {
+      cuuint64_t dims[3] = {(cuuint64_t)ly.cout, (cuuint64_t)rows_padded(lout), (cuuint64_t)batch};
+      cuuint64_t strides[2] = {(cuuint64_t)ly.cout * 2, (cuuint64_t)rows_padded(lout) * ly.cout * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)BM, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, buf[res_buf], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(residual) failed for layer %zu: %d", i, (int)r);
+      r = encode(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, buf[dst], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(result) failed for layer %zu: %d", i, (int)r);
+    }
     AA_REQUIRE(smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);
     const int grid = (int)std::min<long long>(a.tiles, aa::num_sms());
     const int threads = 64 + 128 * a.n_epi;
     AA_REQUIRE(last || ly.elu, "bf16 layers without ELU are not supported on the tensor-core path (layer %zu)", i);
     const bool res = a.res != nullptr;
     if (p.bk == 64) {
-      if (res) conv_tc_kernel<64, true><<<grid, threads, smem, stream>>>(tmA, tmB, a);
-      else conv_tc_kernel<64, false><<<grid, threads, smem, stream>>>(tmA, tmB, a);
+      if (res) conv_tc_kernel<64, true><<<grid, threads, smem, stream>>>(tmA, tmB, tmR, tmO, a);
+      else conv_tc_kernel<64, false><<<grid, threads, smem, stream>>>(tmA, tmB, tmR, tmO, a);
     } else {
-      if (res) conv_tc_kernel<32, true><<<grid, threads, smem, stream>>>(tmA, tmB, a);
-      else conv_tc_kernel<32, false><<<grid, threads, smem, stream>>>(tmA, tmB, a);
+      if (res) conv_tc_kernel<32, true><<<grid, threads, smem, stream>>>(tmA, tmB, tmR, tmO, a);
+      else conv_tc_kernel<32, false><<<grid, threads, smem, stream>>>(tmA, tmB, tmR, tmO, a);
     }
     AA_LAUNCH_CHECK();
     if (ly.role == ROLE_RES_SECOND) res_buf = -1;
