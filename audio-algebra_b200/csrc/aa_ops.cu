@@ -507,6 +507,13 @@ inline int parts_for(long long n) {
 
 }  // namespace
 
+namespace aa {   // csrc/cov_tc.cu
+bool cov_tc_eligible(const float* z, const float* stats, int64_t b, int64_t d);
+int cov_tc_splits(int64_t b, int64_t d);
+int gram_bb_tc(const float* z, const float* mean, int64_t b, int64_t d, float* parts, int splits, cudaStream_t stream);
+int cov_bwd_tc(const float* z, const float* stats, const float* gram, int64_t b, int64_t d, const float* gloss, float gscale, float* gz,
+               int accumulate, cudaStream_t stream);
+}
 namespace aa {   // csrc/gram_tc.cu
 int64_t gram_tc_workspace_floats();
 int gram_tc(const float* y, int64_t b, int64_t t, float* cov_num, double* count, float* workspace, cudaStream_t stream);
@@ -637,7 +644,7 @@ static int cov_splits(int64_t b, int64_t d) {
 }
 
 int64_t aa_cov_loss_workspace_floats(int64_t b, int64_t d) {
-  return aa_reduce_workspace_floats() + (int64_t)cov_splits(b, d) * b * b;
+  return aa_reduce_workspace_floats() + (int64_t)std::max(cov_splits(b, d), aa::cov_tc_splits(b, d)) * b * b;
 }
 
 int aa_vicreg_cov_fwd_f32(const float* z, int64_t b, int64_t d, const float* stats, float* stats_out, float* gram, float* loss,
@@ -651,14 +658,21 @@ int aa_vicreg_cov_fwd_f32(const float* z, int64_t b, int64_t d, const float* sta
     if (rc != AA_OK) return rc;
     stats = stats_out;
   }
-  const int splits = cov_splits(b, d);
-  long long dps = (d + splits - 1) / splits;
-  dps = (dps + GK - 1) / GK * GK;
   float* red = workspace;
   float* gparts = workspace + aa_reduce_workspace_floats();
-  const int nt = (int)((b + GT - 1) / GT);
-  gram_part_kernel<<<dim3(nt, nt, splits), 256, 0, st>>>(z, stats, (int)b, d, dps, gparts);
-  AA_LAUNCH_CHECK();
+  int splits;
+  if (aa::cov_tc_eligible(z, stats, b, d)) {   // B x B x D Gram on tcgen05 (3-term TF32 split, csrc/cov_tc.cu)
+    splits = aa::cov_tc_splits(b, d);
+    int rc = aa::gram_bb_tc(z, stats, b, d, gparts, splits, st);
+    if (rc != AA_OK) return rc;
+  } else {
+    splits = cov_splits(b, d);
+    long long dps = (d + splits - 1) / splits;
+    dps = (dps + GK - 1) / GK * GK;
+    const int nt = (int)((b + GT - 1) / GT);
+    gram_part_kernel<<<dim3(nt, nt, splits), 256, 0, st>>>(z, stats, (int)b, d, dps, gparts);
+    AA_LAUNCH_CHECK();
+  }
   const int p1 = parts_for(b * b);
   gram_reduce_kernel<<<p1, kRedThreads, 0, st>>>(gparts, splits, (int)b, gram, red);
   AA_LAUNCH_CHECK();
@@ -675,6 +689,8 @@ int aa_vicreg_cov_bwd_f32(const float* z, const float* stats, const float* gram,
                           float gscale, float* grad_z, int accumulate, void* stream) {
   AA_REQUIRE(z && stats && gram && grad_z, "NULL argument");
   AA_REQUIRE(b >= 2 && d >= 1 && b < 65536, "bad shape");
+  if (aa::cov_tc_eligible(z, stats, b, d) && b % 4 == 0 && ((uintptr_t)gram & 15) == 0 && ((uintptr_t)grad_z & 15) == 0)
+    return aa::cov_bwd_tc(z, stats, gram, b, d, gloss, gscale, grad_z, accumulate, (cudaStream_t)stream);
   const long long ct = (d + GT - 1) / GT;
   AA_REQUIRE(ct < (1LL << 31), "d too large");
   cov_bwd_kernel<<<dim3((unsigned)ct, (unsigned)((b + GT - 1) / GT)), 256, 0, (cudaStream_t)stream>>>(

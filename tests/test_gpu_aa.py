@@ -163,6 +163,29 @@ def test_cov_loss_training_size_is_cheap_and_consistent(aab):
     assert abs(fd - an) < 2e-2 * max(abs(an), 1e-6)
 
 
+@pytest.mark.parametrize("b,d", [(512, 32768), (200, 4096), (130, 2048), (64, 1028), (256, 5000)])
+def test_cov_loss_tcgen05_gram_and_backward(aab, b, d):
+    """B x B x D Gram (split over D) and the G Xc backward on tcgen05 (csrc/cov_tc.cu: 3-term TF32 split, the backward's Xc operand
+    MN-major in the SWIZZLE_128B / 32-byte-atom layout): loss and gradient against the float64 closed form, incl. batch sizes that
+    are not tile multiples (zero-padded rows), b % 4 != 0 (forward on the tensor core, backward on the CUDA-core kernel) and a
+    feature count that is not a chunk multiple."""
+    g = torch.Generator(device="cuda").manual_seed(b + d)
+    z = torch.randn(b, d, device="cuda", generator=g) * torch.linspace(0.2, 2.0, d, device="cuda") + 0.5
+    z = z + 0.6 * torch.roll(z, 1, dims=1)   # correlated neighbouring columns
+    zc = z.clone().reshape(b, 1, d).requires_grad_(True)
+    loss = aab.vicreg_cov_loss(zc)
+    loss.backward()
+    x = z.double()
+    xc = x - x.mean(0, keepdim=True)
+    gram = xc @ xc.T
+    s = (xc * xc).sum(0)
+    k = 1.0 / ((b - 1) ** 2 * d)
+    ref = ((gram ** 2).sum() - (s ** 2).sum()) * k
+    gref = 4.0 * k * (gram @ xc - xc * s)
+    assert abs(loss.item() - ref.item()) < 2e-5 * abs(ref.item()), (loss.item(), ref.item())
+    assert rel_l2(zc.grad.reshape(b, d), gref) < 2e-5
+
+
 def test_latent_ops(aab):
     O = _oracle()
     from audio_algebra_b200 import latent_ops as L
