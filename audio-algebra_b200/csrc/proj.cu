@@ -329,6 +329,12 @@ constexpr int kBwdSmem = (4 * PD * WLD + 4 * PD + (4 + 3 + 4) * PD * TSD) * 4;
 
 namespace aa {
 int proj_fwd_tc(const float* const* w, const float* const* b, const float* x, int64_t batch, int64_t t, float* out, cudaStream_t stream);
+// csrc/proj_bwd_tc.cu
+int64_t proj_bwd_tc_workspace_floats();
+bool proj_bwd_tc_enabled();
+int proj_bwd_tc(const float* const* w, const float* const* b, const float* x, const float* gout, int64_t batch, int64_t t, float* gx,
+                int accumulate_gx, float* const* gw, float* const* gb, int accumulate_gw, float gscale, float* workspace,
+                cudaStream_t stream);
 }
 
 extern "C" {
@@ -355,7 +361,9 @@ int aa_projector_half_fwd_f32(const float* const* w_host, const float* const* b_
   return AA_OK;
 }
 
-int64_t aa_projector_bwd_workspace_floats(void) { return (int64_t)aa::num_sms() * 4 * (PD * PD + PD); }
+int64_t aa_projector_bwd_workspace_floats(void) {
+  return std::max<int64_t>((int64_t)aa::num_sms() * 4 * (PD * PD + PD), aa::proj_bwd_tc_workspace_floats());
+}
 
 int aa_projector_half_bwd_f32(const float* const* w_host, const float* const* b_host, int dims, int hidden, int resid,
                               const float* x, const float* gout, int64_t batch, int64_t t, float* gx, int accumulate_gx,
@@ -366,6 +374,16 @@ int aa_projector_half_bwd_f32(const float* const* w_host, const float* const* b_
   if (rc != AA_OK) return rc;
   AA_REQUIRE(gout && workspace && gw_host && gb_host, "NULL argument");
   if (ba.f.n_tiles == 0) return AA_OK;
+  // the standard 64 -> 64 residual projector runs on the tensor core (tcgen05, bf16x3 split: fp32-accurate, proj_bwd_tc.cu);
+  // other shapes and AA_PROJ_FP32=1 / AA_PROJ_BWD_TC=0 use the CUDA-core kernel below
+  {
+    static const bool force_fp32 = getenv("AA_PROJ_FP32") != nullptr;
+    bool ok = !force_fp32 && aa::proj_bwd_tc_enabled() && dims == PD && hidden == PD && resid && t >= 64;
+    for (int l = 0; l < 4 && ok; ++l) ok = (reinterpret_cast<uintptr_t>(w_host[l]) & 15) == 0 && gw_host[l] != nullptr && gb_host[l] != nullptr;
+    if (ok)
+      return aa::proj_bwd_tc(w_host, b_host, x, gout, batch, t, gx, accumulate_gx, gw_host, gb_host, accumulate_gw, gscale, workspace,
+                             (cudaStream_t)stream);
+  }
   AA_CUDA(aa::ensure_dyn_smem(proj_bwd_kernel, kBwdSmem));   // per (kernel, device)
   ba.gout = gout; ba.gx = gx; ba.partials = workspace; ba.accumulate_gx = accumulate_gx;
   const int grid = (int)std::min<long long>(ba.f.n_tiles, (long long)aa::num_sms());
