@@ -116,6 +116,37 @@ def test_loss_gradients_golden(aab, golden):
     assert rel_l2(a.grad, g["grad_mse_a"]) < 1e-5
 
 
+@pytest.mark.parametrize("b,t", [(160, 640), (9, 1000), (3, 200)])
+def test_projector_backward_tcgen05_many_tiles(aab, b, t):
+    """csrc/proj_bwd_tc.cu (bf16x3 pieces, K-major + MN-major views of one SWIZZLE_128B copy, weight-gradient accumulators in TMEM):
+    several tiles per CTA incl. the periodic accumulator drain (160 x 640: 800 tiles on 148 CTAs), ragged last tiles, against a
+    float64 torch restatement of the four blocks; both halves (encode and decode) are exercised."""
+    torch.manual_seed(b + t)
+    aa = aab.AudioAlgebra(64, 64).cuda()
+    y = (0.7 * torch.randn(b, 64, t, device="cuda")).requires_grad_(True)
+    gz, gy = torch.randn(b, 64, t, device="cuda"), torch.randn(b, 64, t, device="cuda")
+    z, yr = aa(y)
+    ((z * gz).sum() + (yr * gy).sum()).backward()
+
+    def half(seq, xin):
+        ws = [(blk.lin.weight.detach().double().requires_grad_(True), blk.lin.bias.detach().double().requires_grad_(True)) for blk in seq]
+        h = xin.transpose(1, 2)
+        for i, (w, bb) in enumerate(ws):
+            u = h @ w.T + bb
+            h = h + (torch.nn.functional.gelu(u) if i < 3 else u)
+        return xin + h.transpose(1, 2), ws
+
+    yd = y.detach().double().requires_grad_(True)
+    zd, we = half(aa.encoder, yd)
+    yrd, wd = half(aa.decoder, zd)
+    ((zd * gz.double()).sum() + (yrd * gy.double()).sum()).backward()
+    assert rel_l2(z, zd) < 1e-5 and rel_l2(yr, yrd) < 1e-5
+    assert rel_l2(y.grad, yd.grad) < 1e-5
+    for seq, ws in ((aa.encoder, we), (aa.decoder, wd)):
+        for blk, (w, bb) in zip(seq, ws):
+            assert rel_l2(blk.lin.weight.grad, w.grad) < 2e-5 and rel_l2(blk.lin.bias.grad, bb.grad) < 1e-5
+
+
 @pytest.mark.parametrize("b,c,t", [(2, 3, 5), (16, 64, 16), (33, 8, 40), (96, 64, 64)])
 def test_cov_and_var_vs_naive_oracle(aab, b, c, t):
     "Gram-identity covariance loss == the reference's materialised (C T)^2 covariance (small T only)"
