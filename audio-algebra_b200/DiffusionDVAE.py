@@ -53,7 +53,8 @@ class _Handles:
     "per-device AaEncoder handles + upload bookkeeping; deliberately NOT copied by deepcopy"
 
     def __init__(self):
-        self.h, self.versions, self.ws = {}, {}, {}
+        self.h, self.versions, self.ws = {}, {}, {}   # ws: one activation workspace per (device, stream)
+        self.w_event = {}   # per device: recorded after the last weight upload; other streams wait on it before a forward
 
     def __deepcopy__(self, memo):
         return _Handles()
@@ -134,6 +135,11 @@ class SoundStreamXLEncoder(nn.Module):
                 w, b = _f32c(c.weight.detach()), _f32c(c.bias.detach())
                 check(lib.aa_encoder_set_weights(h, i, ptr(w), ptr(b), stream_ptr()))
             H.versions[dev] = ver
+            ev = torch.cuda.Event()
+            ev.record()
+            H.w_event[dev] = (ev, torch.cuda.current_stream().cuda_stream)
+        elif dev in H.w_event and H.w_event[dev][1] != torch.cuda.current_stream().cuda_stream:
+            torch.cuda.current_stream().wait_event(H.w_event[dev][0])   # weights were uploaded on another stream
         return h
 
     def out_length(self, n):
@@ -161,10 +167,11 @@ class SoundStreamXLEncoder(nn.Module):
             if b == 0:
                 return y
             nbytes = int(lib.aa_encoder_workspace_bytes(h, b, n, dt))
-            ws = self._handles.ws.get(dev)
+            wkey = (dev, torch.cuda.current_stream().cuda_stream)   # callers on different streams must not share activations
+            ws = self._handles.ws.get(wkey)
             if ws is None or ws.numel() < nbytes:
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=x0.device)
-                self._handles.ws[dev] = ws
+                self._handles.ws[wkey] = ws
             pa, keep = _ptr_array(stems)
             fa = (C.c_float * len(stems))(*fl)
             check(lib.aa_encoder_forward(h, pa, fa, len(stems), b, n, int(apply_tanh), dt, ptr(y), ptr(ws), stream_ptr()))

@@ -492,3 +492,21 @@ def test_dvae_checkpoint_loader(tmp_path):
     torch.save({"state_dict": sd}, path)
     with pytest.raises(RuntimeError):
         load_dvae_encoder_checkpoint(aab.DVAEWrapper(debug=False).model, str(path))
+
+
+def test_encode_on_two_streams_does_not_share_activations(setup):
+    """Two CUDA streams driving the same encoder concurrently (one activation workspace per (device, stream); the stream that did
+    not upload the weights waits on the upload's event): results equal the sequential ones bit for bit."""
+    aab, O, enc_o, dv = setup
+    xa, xb = _x((6, 2, 32768), 31).cuda(), _x((6, 2, 32768), 32).cuda()
+    ya, yb = dv.encode(xa).clone(), dv.encode(xb).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = {}
+    for _ in range(3):   # several rounds: the kernels of the two streams overlap on the device
+        with torch.cuda.stream(s1):
+            outs["a"] = dv.encode(xa)
+        with torch.cuda.stream(s2):
+            outs["b"] = dv.encode(xb)
+    torch.cuda.synchronize()
+    assert torch.equal(outs["a"], ya) and torch.equal(outs["b"], yb)
