@@ -4,7 +4,7 @@ train_aa_effects.py:58-98 (L2-hinge variance loss :42-46)."""
 import torch
 
 from .aa_mixer import (EmbedBlock, AudioAlgebra, mseloss, vicreg_var_loss, vicreg_var_loss_l2, vicreg_cov_loss,  # noqa: F401
-                       off_diagonal, _lincomb_ad)
+                       off_diagonal, _lincomb_ad, effects_loss_fused)
 
 __all__ = ['EmbedBlock', 'AudioAlgebra', 'do_mixing', 'mseloss', 'vicreg_var_loss', 'vicreg_var_loss_l2',
            'vicreg_cov_loss', 'off_diagonal', 'effects_guesses', 'effects_losses']
@@ -31,8 +31,12 @@ def effects_guesses(za1, zb1, za2, zb2):
     return _lincomb_ad([zb2, zb1, za1], [1.0, -1.0, 1.0]), _lincomb_ad([za2, za1, zb1], [1.0, -1.0, 1.0])
 
 
-def effects_losses(archive):
-    "loss terms of AAEffectsModule.training_step (train_aa_effects.py:66-82)"
+def effects_losses(archive, fused=True):
+    """loss terms of AAEffectsModule.training_step (train_aa_effects.py:66-82).  fused (default): one aa_effects_loss_fwd_f32 /
+    _bwd_f32 call each way; fused=False assembles the same terms from the standalone loss Functions (the tests compare the two)."""
+    if fused:
+        return effects_loss_fused([z.float() for z in archive["zs"]], [y.float() for y in archive["ys"]],
+                                  [r.float() for r in archive["yrecons"]])
     za1, zb1, za2, zb2 = [z.float() for z in archive["zs"]]
     za2_guess, zb2_guess = effects_guesses(za1, zb1, za2, zb2)
     mix_loss = (mseloss(za2_guess, za2) + mseloss(zb2_guess, zb2)) / 2

@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 
 __all__ = ['EmbedBlock', 'AudioAlgebra', 'get_stems_faders', 'do_mixing', 'mseloss', 'vicreg_var_loss',
-           'vicreg_cov_loss', 'off_diagonal', 'latent_lincomb']
+           'vicreg_cov_loss', 'off_diagonal', 'latent_lincomb', 'mixer_loss_fused', 'effects_loss_fused']
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pp = C.POINTER(C.c_void_p)
@@ -43,6 +43,13 @@ _lib.register({
     "aa_embed_block_bwd_f32": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "aa_batchnorm_fwd_f32": (_i, [_p, _i64, _i, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p]),
     "aa_batchnorm_bwd_f32": (_i, [_p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _p]),
+    "aa_mixer_loss_saved_floats": (_i64, [_i64, _i64]),
+    "aa_effects_loss_saved_floats": (_i64, [_i64, _i64]),
+    "aa_fused_loss_workspace_floats": (_i64, [_i64, _i64]),
+    "aa_mixer_loss_fwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _f, _p, _p, _p, _p]),
+    "aa_mixer_loss_bwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "aa_effects_loss_fwd_f32": (_i, [_pp, _pp, _pp, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p]),
+    "aa_effects_loss_bwd_f32": (_i, [_pp, _pp, _pp, _i64, _i64, _i64, _f, _f, _p, _p, _pp, _pp, _p]),
 })
 
 _RED_WS = int(lib.aa_reduce_workspace_floats())
@@ -195,6 +202,95 @@ class _CovLoss(torch.autograd.Function):
         with torch.cuda.device(z.device):
             check(lib.aa_vicreg_cov_bwd_f32(ptr(z), ptr(stats), ptr(gram), b, d, ptr(g), 1.0, ptr(gz), 0, stream_ptr()))
         return gz
+
+
+def _as_bct(t: Tensor, what):
+    t = _f32c(t, what)
+    assert t.dim() >= 2, f"{what}: expected [B, ...], got {tuple(t.shape)}"
+    return t
+
+
+class _MixerLossFused(torch.autograd.Function):
+    """aa_mixer_loss_fwd/bwd_f32: every term of train_aa_mixer_accel.py:504-517 in one C call each way."""
+
+    @staticmethod
+    def forward(ctx, zsum, zmix, y, yrecon, ymix, ymix_recon, hinge_l2, gamma, eps):
+        ts = [_as_bct(v, n) for v, n in ((zsum, "zsum"), (zmix, "zmix"), (y, "y"), (yrecon, "yrecon"), (ymix, "ymix"), (ymix_recon, "ymix_recon"))]
+        assert all(v.shape == ts[0].shape for v in ts), "mixer loss: all six tensors must have one shape"
+        b, d = ts[0].shape[0], ts[0].numel() // ts[0].shape[0]
+        dev = ts[0].device
+        losses = torch.empty(5, dtype=torch.float32, device=dev)
+        saved = torch.empty(int(lib.aa_mixer_loss_saved_floats(b, d)), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(int(lib.aa_fused_loss_workspace_floats(b, d)), dev)
+            check(lib.aa_mixer_loss_fwd_f32(*[ptr(v) for v in ts], b, 1, d, int(hinge_l2), float(gamma), float(eps), ptr(losses), ptr(saved),
+                                            ptr(ws), stream_ptr()))
+        ctx.save_for_backward(*ts, saved)
+        ctx.cfg = (b, d, int(hinge_l2), float(gamma), float(eps))
+        terms = losses[1:].clone()
+        ctx.mark_non_differentiable(terms)
+        return losses[0], terms
+
+    @staticmethod
+    def backward(ctx, g, _g_terms):
+        *ts, saved = ctx.saved_tensors
+        b, d, l2, gamma, eps = ctx.cfg
+        g = g.contiguous().float()
+        outs = [torch.empty_like(ts[0]) for _ in range(4)]
+        with torch.cuda.device(ts[0].device):
+            check(lib.aa_mixer_loss_bwd_f32(*[ptr(v) for v in ts], b, 1, d, l2, gamma, eps, ptr(saved), ptr(g), *[ptr(o) for o in outs],
+                                            stream_ptr()))
+        return outs[0], outs[1], None, outs[2], None, outs[3], None, None, None
+
+
+def mixer_loss_fused(zsum, zmix, y, yrecon, ymix, ymix_recon, hinge_l2=False, gamma=1.0, eps=1e-4):
+    """All loss terms of the mixer training step (train_aa_mixer_accel.py:504-517) through the fused C entry points:
+    returns the dict {'loss', 'mix_loss', 'var_loss', 'cov_loss', 'aa_recon_loss'}; only 'loss' carries gradient
+    (to zsum, zmix, yrecon, ymix_recon -- y and ymix come from the frozen given model)."""
+    loss, terms = _MixerLossFused.apply(zsum, zmix, y, yrecon, ymix, ymix_recon, hinge_l2, gamma, eps)
+    return {'loss': loss, 'mix_loss': terms[0], 'var_loss': terms[1], 'cov_loss': terms[2], 'aa_recon_loss': terms[3]}
+
+
+class _EffectsLossFused(torch.autograd.Function):
+    """aa_effects_loss_fwd/bwd_f32: every term of train_aa_effects.py:66-82 in one C call each way."""
+
+    @staticmethod
+    def forward(ctx, gamma, eps, *tensors):   # za1, zb1, za2, zb2, y x 4, yrecon x 4
+        ts = [_as_bct(v, "effects loss input") for v in tensors]
+        assert len(ts) == 12 and all(v.shape == ts[0].shape for v in ts)
+        b, d = ts[0].shape[0], ts[0].numel() // ts[0].shape[0]
+        dev = ts[0].device
+        losses = torch.empty(5, dtype=torch.float32, device=dev)
+        saved = torch.empty(int(lib.aa_effects_loss_saved_floats(b, d)), dtype=torch.float32, device=dev)
+        zp, k1 = _ptr_array(ts[0:4]); yp, k2 = _ptr_array(ts[4:8]); rp, k3 = _ptr_array(ts[8:12])
+        with torch.cuda.device(dev):
+            ws = _ws(int(lib.aa_fused_loss_workspace_floats(b, d)), dev)
+            check(lib.aa_effects_loss_fwd_f32(zp, yp, rp, b, 1, d, float(gamma), float(eps), ptr(losses), ptr(saved), ptr(ws), stream_ptr()))
+        ctx.save_for_backward(*ts, saved)
+        ctx.cfg = (b, d, float(gamma), float(eps))
+        terms = losses[1:].clone()
+        ctx.mark_non_differentiable(terms)
+        return losses[0], terms
+
+    @staticmethod
+    def backward(ctx, g, _g_terms):
+        *ts, saved = ctx.saved_tensors
+        b, d, gamma, eps = ctx.cfg
+        g = g.contiguous().float()
+        gz = [torch.empty_like(ts[0]) for _ in range(4)]
+        gr = [torch.empty_like(ts[0]) for _ in range(4)]
+        zp, k1 = _ptr_array(ts[0:4]); yp, k2 = _ptr_array(ts[4:8]); rp, k3 = _ptr_array(ts[8:12])
+        gzp, k4 = _ptr_array(gz); grp, k5 = _ptr_array(gr)
+        with torch.cuda.device(ts[0].device):
+            check(lib.aa_effects_loss_bwd_f32(zp, yp, rp, b, 1, d, gamma, eps, ptr(saved), ptr(g), gzp, grp, stream_ptr()))
+        return (None, None) + tuple(gz) + (None,) * 4 + tuple(gr)
+
+
+def effects_loss_fused(zs, ys, yrecons, gamma=1.0, eps=1e-4):
+    """All loss terms of the effects training step (train_aa_effects.py:66-82, L2-hinge variance loss) through the fused C entry
+    points; zs = [za1, zb1, za2, zb2], ys / yrecons likewise.  Only 'loss' carries gradient (to zs and yrecons)."""
+    loss, terms = _EffectsLossFused.apply(gamma, eps, *zs, *ys, *yrecons)
+    return {'loss': loss, 'mix_loss': terms[0], 'var_loss': terms[1], 'cov_loss': terms[2], 'aa_recon_loss': terms[3]}
 
 
 def vicreg_cov_loss(z: Tensor) -> Tensor:

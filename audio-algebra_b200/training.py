@@ -9,7 +9,7 @@ import torch
 
 from ._lib import lib, check, ptr, stream_ptr
 from .parallel import allreduce_mean_
-from .aa_mixer import (AudioAlgebra, do_mixing, get_stems_faders, mseloss, vicreg_var_loss, vicreg_cov_loss)  # noqa: F401
+from .aa_mixer import (AudioAlgebra, do_mixing, get_stems_faders, mseloss, vicreg_var_loss, vicreg_cov_loss, mixer_loss_fused)  # noqa: F401
 
 __all__ = ['FlatAdam', 'onecycle_lr', 'onecycle_beta1', 'mixer_losses', 'MixerTrainer', 'save_aa_checkpoint', 'load_aa_checkpoint']
 
@@ -70,8 +70,11 @@ class FlatAdam:
                                        self.params.numel(), lr, b1, self.betas[1], self.eps, self.t, stream_ptr()))
 
 
-def mixer_losses(zsum, zmix, y, yrecon, ymix, ymix_recon):
-    "train_aa_mixer_accel.py:504-517"
+def mixer_losses(zsum, zmix, y, yrecon, ymix, ymix_recon, fused=True):
+    """train_aa_mixer_accel.py:504-517.  fused (default): one aa_mixer_loss_fwd_f32 / _bwd_f32 call each way; fused=False assembles
+    the same terms from the standalone loss Functions (the tests compare the two)."""
+    if fused:
+        return mixer_loss_fused(zsum, zmix, y, yrecon, ymix, ymix_recon)
     mix_loss = mseloss(zsum, zmix)
     var_loss = (vicreg_var_loss(zsum) + vicreg_var_loss(zmix)) / 2
     cov_loss = (vicreg_cov_loss(zsum) + vicreg_cov_loss(zmix)) / 2

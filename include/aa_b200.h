@@ -277,6 +277,34 @@ int aa_projector_half_bwd_f32(const float* const* w_host, const float* const* b_
                               float* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused loss entry points of the two training steps: one call evaluates every loss term
+ * and one call writes every gradient; the per-term kernels above run back to back on `stream` and
+ * accumulate straight into the gradient buffers.  Replaces train_aa_mixer_accel.py:504-517 (mixer) and
+ * train_aa_effects.py:66-82 (effects; L2-hinge variance loss).  All tensors [B][C][T] f32, d = C*T.
+ * losses[5] (device) = {loss, mix_loss, var_loss, cov_loss, aa_recon_loss} = the reference's log_dict.
+ * saved: >= aa_*_loss_saved_floats(b, d) floats, written by fwd and read by bwd (feature statistics,
+ * Gram matrices, the two effect guesses); workspace: >= aa_fused_loss_workspace_floats(b, d) floats.
+ * bwd: gloss = device scalar dL/dloss or NULL (= 1); every gradient output is overwritten; y / ymix / ys
+ * carry no gradient (the given model is frozen).
+ * ------------------------------------------------------------------------------------------ */
+int64_t aa_mixer_loss_saved_floats(int64_t b, int64_t d);
+int64_t aa_effects_loss_saved_floats(int64_t b, int64_t d);
+int64_t aa_fused_loss_workspace_floats(int64_t b, int64_t d);
+int aa_mixer_loss_fwd_f32(const float* zsum, const float* zmix, const float* y, const float* y_recon, const float* ymix,
+                          const float* ymix_recon, int64_t b, int64_t c, int64_t t, int hinge_l2, float gamma, float eps,
+                          float* losses, float* saved, float* workspace, void* stream);
+int aa_mixer_loss_bwd_f32(const float* zsum, const float* zmix, const float* y, const float* y_recon, const float* ymix,
+                          const float* ymix_recon, int64_t b, int64_t c, int64_t t, int hinge_l2, float gamma, float eps,
+                          const float* saved, const float* gloss, float* g_zsum, float* g_zmix, float* g_y_recon,
+                          float* g_ymix_recon, void* stream);
+/* zs = {za1, zb1, za2, zb2}; ys / yrecons / g_zs / g_yrecons likewise: host arrays of 4 device pointers */
+int aa_effects_loss_fwd_f32(const float* const* zs, const float* const* ys, const float* const* yrecons, int64_t b, int64_t c,
+                            int64_t t, float gamma, float eps, float* losses, float* saved, float* workspace, void* stream);
+int aa_effects_loss_bwd_f32(const float* const* zs, const float* const* ys, const float* const* yrecons, int64_t b, int64_t c,
+                            int64_t t, float gamma, float eps, const float* saved, const float* gloss, float* const* g_zs,
+                            float* const* g_yrecons, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * PCA accumulation (calc_effects_pca.py:81-89): y [B][C][T] f32 -> cov_num [C][C] += C-by-C
  * batch-centred scatter of the B*T points; count += B*T.  (eigh of the 64x64 result stays on host.)
  * workspace: >= C*C*grid + 2*C floats, see aa_cov_workspace_floats.

@@ -96,3 +96,50 @@ def test_projector_and_loss_outputs_stay_inside_their_buffers():
         check(lib.aa_latent_lincomb_f32(2, arr, ca, ptr(out), x.numel(), stream_ptr()))
         torch.cuda.synchronize()
         _check(buf, x.numel(), g, f"lincomb b={b} t={t}")
+
+
+def test_tcgen05_backward_kernels_stay_inside_their_buffers():
+    """Round-2 tensor-core kernels: projector backward (gx, four weight / bias gradients, the per-CTA partial workspace) and the
+    covariance loss Gram / backward (gram, grad_z, the split-K workspace) at ragged shapes."""
+    import audio_algebra_b200 as aab
+    from audio_algebra_b200._lib import lib, check, ptr, stream_ptr
+    from audio_algebra_b200.aa_mixer import _ptr_array
+    torch.manual_seed(3)
+    aa = aab.AudioAlgebra(64, 64).cuda()
+    ws = [blk.lin.weight.detach().contiguous() for blk in aa.encoder]
+    bs = [blk.lin.bias.detach().contiguous() for blk in aa.encoder]
+    wp, k1 = _ptr_array(ws)
+    bp, k2 = _ptr_array(bs)
+    nws = int(lib.aa_projector_bwd_workspace_floats())
+    for b, t in [(3, 70), (2, 1000), (150, 129)]:
+        x, gout = torch.randn(b, 64, t, device="cuda"), torch.randn(b, 64, t, device="cuda")
+        gbuf, gx, g = _guarded(x.numel())
+        wsbuf, wsp, gw_ = _guarded(nws)
+        gws = [_guarded(64 * 64) for _ in range(4)]
+        gbs = [_guarded(64) for _ in range(4)]
+        gwp, k3 = _ptr_array([q[1] for q in gws])
+        gbp, k4 = _ptr_array([q[1] for q in gbs])
+        check(lib.aa_projector_half_bwd_f32(wp, bp, 64, 64, 1, ptr(x), ptr(gout), b, t, ptr(gx), 0, gwp, gbp, 0, 1.0, ptr(wsp), stream_ptr()))
+        torch.cuda.synchronize()
+        _check(gbuf, x.numel(), g, f"projector bwd gx b={b} t={t}")
+        _check(wsbuf, nws, gw_, f"projector bwd workspace b={b} t={t}", payload_written=False)
+        for i in range(4):
+            _check(gws[i][0], 64 * 64, gws[i][2], f"projector bwd gw{i}")
+            _check(gbs[i][0], 64, gbs[i][2], f"projector bwd gb{i}")
+    for b, d in [(130, 2052), (64, 1024), (200, 4096)]:
+        z = torch.randn(b, d, device="cuda")
+        nws = int(lib.aa_cov_loss_workspace_floats(b, d))
+        wsbuf, wsp, gw_ = _guarded(nws)
+        sbuf, stats, gs = _guarded(2 * d)
+        grbuf, gram, gg = _guarded(b * b)
+        lbuf, loss, gl = _guarded(1)
+        check(lib.aa_vicreg_cov_fwd_f32(ptr(z), b, d, None, ptr(stats), ptr(gram), ptr(loss), ptr(wsp), stream_ptr()))
+        torch.cuda.synchronize()
+        _check(wsbuf, nws, gw_, f"cov fwd workspace b={b} d={d}", payload_written=False)
+        _check(sbuf, 2 * d, gs, f"cov fwd stats b={b} d={d}")
+        _check(grbuf, b * b, gg, f"cov fwd gram b={b} d={d}")
+        _check(lbuf, 1, gl, "cov fwd loss")
+        gzbuf, gz, gz_ = _guarded(b * d)
+        check(lib.aa_vicreg_cov_bwd_f32(ptr(z), ptr(stats), ptr(gram), b, d, None, 1.0, ptr(gz), 0, stream_ptr()))
+        torch.cuda.synchronize()
+        _check(gzbuf, b * d, gz_, f"cov bwd grad_z b={b} d={d}")

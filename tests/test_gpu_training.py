@@ -112,3 +112,38 @@ def test_effects_step_matches_oracle(setup):
     assert rel_l2(g, g_ref) < 5e-3
     for i in range(4):
         assert rel_l2(arch["ys"][i], ys[i]) < 1e-3 and rel_l2(arch["zs"][i], zs[i]) < 1e-3
+
+
+def test_fused_loss_entry_points_match_the_assembled_losses():
+    """aa_mixer_loss_fwd/bwd_f32 and aa_effects_loss_fwd/bwd_f32 (one C call per direction) against the same terms
+    assembled from the standalone loss Functions: every log_dict entry and every gradient."""
+    import audio_algebra_b200 as aab
+    from audio_algebra_b200.training import mixer_losses
+    g = torch.Generator(device="cuda").manual_seed(11)
+    b, c, t = 96, 64, 32
+
+    def mk():
+        return (0.8 * torch.randn(b, c, t, device="cuda", generator=g) + 0.1)
+
+    base = [mk() for _ in range(6)]
+    res = {}
+    for fused in (True, False):
+        zsum, zmix, y, yrecon, ymix, ymix_recon = [v.clone().requires_grad_(i in (0, 1, 3, 5)) for i, v in enumerate(base)]
+        L = mixer_losses(zsum, zmix, y, yrecon, ymix, ymix_recon, fused=fused)
+        (1.7 * L["loss"]).backward()
+        res[fused] = ({k: float(v.detach()) for k, v in L.items()}, [zsum.grad, zmix.grad, yrecon.grad, ymix_recon.grad])
+    for k in res[True][0]:
+        assert abs(res[True][0][k] - res[False][0][k]) <= 2e-6 * abs(res[False][0][k]), k
+    for ga, gb in zip(res[True][1], res[False][1]):
+        assert rel_l2(ga, gb) < 2e-6
+    base = [mk() for _ in range(12)]
+    res = {}
+    for fused in (True, False):
+        ts = [v.clone().requires_grad_(i < 4 or i >= 8) for i, v in enumerate(base)]
+        L = aab.aa_effects.effects_losses({"zs": ts[0:4], "ys": ts[4:8], "yrecons": ts[8:12]}, fused=fused)
+        (0.6 * L["loss"]).backward()
+        res[fused] = ({k: float(v.detach()) for k, v in L.items()}, [v.grad for v in ts[0:4] + ts[8:12]])
+    for k in res[True][0]:
+        assert abs(res[True][0][k] - res[False][0][k]) <= 2e-6 * abs(res[False][0][k]), k
+    for ga, gb in zip(res[True][1], res[False][1]):
+        assert rel_l2(ga, gb) < 2e-6
