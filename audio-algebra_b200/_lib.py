@@ -39,6 +39,11 @@ _SIGS = {
     "aa_stft_mel_tf_f32_host": (_i, [_p, _p, _i64, _i64, _i, _p, _i64]),
     "aa_magdphase_f32": (_i, [_p, _i64, _i64, _i64, _p, _p]),
     "aa_magdphase_ex_f32": (_i, [_p, _i64, _i64, _i64, _i, _i, _p, _p]),
+    "aa_istft_workspace_floats": (_i64, [_i64, _i, _i64]),
+    "aa_istft_f32": (_i, [_p, _i64, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p]),
+    "aa_griffinlim_update_c64": (_i, [_p, _p, _p, _p, _i64, C.c_float, _i, _p]),
+    "aa_inverse_mel_f32": (_i, [_p, _p, _i64, _i, _i, _i64, _i64, _i64, _i64, _p, _p]),
+    "aa_magdphase_decode_f32": (_i, [_p, _i64, _i64, _i64, _i, _p, _p, _p]),
     "aa_stft_mel_f32_host": (_i, [_p, _p, _i64, _i64, _i, _p, _i64]),
 }
 

@@ -38,10 +38,10 @@ class GivenModelClass(nn.Module):
         return None
 
     def decode(self, reps: torch.Tensor, **kwargs) -> torch.Tensor:
-        raise NotImplementedError(f"{self.name}.decode is outside the accelerated hot path (encode side only)")
+        raise NotImplementedError(f"{self.name}.decode: the generative decoders (diffusion sample() loops) are outside the accelerated path")
 
     def forward(self, waveform: torch.Tensor):
-        "reference returns (reps, recons); recons needs the decoder, which is out of scope here"
+        "given_models.py:79-82: (reps, recons)"
         reps = self.encode(waveform)
         return (reps, self.decode(reps))
 
@@ -271,6 +271,72 @@ class _StftFrontEnd(GivenModelClass):
         return out.cpu() if on_cpu else out
 
 
+    # ---- decoder side (round-trip demos) -------------------------------------------------------------
+    def _istft(self, spec: torch.Tensor) -> torch.Tensor:
+        """torch.istft / T.InverseSpectrogram(n_fft, hop, center, window) of a complex [..., F, T] tensor (any strides: the
+        transposed view encode() returns is read in place) -> [..., hop * (T - 1)] float32 on spec's device."""
+        if not spec.is_complex():
+            raise TypeError("expected a complex spectrogram")
+        if self.n_fft > 4096:
+            raise NotImplementedError("the inverse STFT supports n_fft <= 4096")
+        on_cpu = not spec.is_cuda
+        dev = _lib.ensure_device(None if on_cpu else spec.device)
+        with torch.cuda.device(dev):
+            z = spec.to(f"cuda:{dev}").to(torch.complex64)
+            lead, (f, t) = z.shape[:-2], z.shape[-2:]
+            assert f == self.n_fft // 2 + 1, f"expected {self.n_fft // 2 + 1} frequency bins, got {f}"
+            rows = int(math.prod(lead)) if len(lead) else 1
+            z3 = z.reshape(rows, f, t) if z.dim() != 3 else z     # views keep the [T][F] memory of torch.stft's own layout
+            if rows > 1 and z3.stride(0) == 0:
+                z3 = z3.contiguous()
+            if not self.center and t * self.hop_length < 1:
+                raise ValueError("empty output")
+            out_len = self.hop_length * (t - 1) if self.center else self.n_fft + self.hop_length * (t - 1)
+            if out_len < 1:
+                raise ValueError("istft needs at least two frames when center=True")
+            out = torch.empty((rows, out_len), dtype=torch.float32, device=z.device)
+            ws = torch.empty(int(lib.aa_istft_workspace_floats(rows, self.n_fft, t)), dtype=torch.float32, device=z.device)
+            win = self.window.to(z.device)
+            check(lib.aa_istft_f32(ptr(z3), rows, self.n_fft, self.hop_length, int(self.center), t, z3.stride(0), z3.stride(1), z3.stride(2),
+                                   ptr(win), ptr(out), out_len, ptr(ws), stream_ptr()))
+            out = out.reshape(*lead, out_len)
+        return out.cpu() if on_cpu else out
+
+    def _griffinlim(self, specgram: torch.Tensor, power=2.0, n_iter=32, momentum=0.99, rand_init=True, init_angles=None) -> torch.Tensor:
+        """torchaudio.functional.griffinlim (T.GriffinLim defaults: power 2, 32 iterations, momentum 0.99, random initial phase)
+        on the CUDA STFT / inverse-STFT kernels.  init_angles (complex [..., F, T]) replaces the random start (tests)."""
+        on_cpu = not specgram.is_cuda
+        dev = _lib.ensure_device(None if on_cpu else specgram.device)
+        with torch.cuda.device(dev):
+            sg = specgram.to(f"cuda:{dev}").float()
+            lead, (f, t) = sg.shape[:-2], sg.shape[-2:]
+            rows = int(math.prod(lead)) if len(lead) else 1
+            mag = sg.reshape(rows, f, t).pow(1.0 / power).transpose(1, 2).contiguous()          # [rows][T][F]: the STFT kernels' layout
+            if init_angles is not None:
+                ang = init_angles.to(sg.device).to(torch.complex64).reshape(rows, f, t).transpose(1, 2).contiguous()
+            elif rand_init:
+                ang = torch.rand((rows, f, t), dtype=torch.complex64, device=sg.device).transpose(1, 2).contiguous()
+            else:
+                ang = torch.ones((rows, t, f), dtype=torch.complex64, device=sg.device)
+            prod = (mag * ang).contiguous()
+            tprev = torch.zeros_like(prod)
+            mom = float(momentum) / (1.0 + float(momentum))
+            saved = (self.zero_pad, self.orig_shape)
+            self.zero_pad = False
+            try:
+                for it in range(n_iter):
+                    inverse = self._istft(prod.transpose(1, 2))
+                    rebuilt = self._run(inverse, "complex")                   # transposed view of a contiguous [rows][T][F] buffer
+                    rb = rebuilt.transpose(-1, -2)
+                    assert rb.is_contiguous() and rb.shape == prod.shape
+                    check(lib.aa_griffinlim_update_c64(ptr(rb), ptr(tprev), ptr(mag), ptr(prod), prod.numel(), mom, int(it == 0), stream_ptr()))
+                wav = self._istft(prod.transpose(1, 2))
+            finally:
+                self.zero_pad, self.orig_shape = saved
+            wav = wav.reshape(*lead, wav.shape[-1])
+        return wav.cpu() if on_cpu else wav
+
+
 class SpectrogramAE(_StftFrontEnd):
     "Raw (complex) spectrogram (given_models.py:149-168); encode -> complex64 [..., n_fft/2+1, frames]"
 
@@ -279,6 +345,10 @@ class SpectrogramAE(_StftFrontEnd):
 
     def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
         return self._run(waveform, "complex")
+
+    def decode(self, reps: torch.Tensor, **kwargs) -> torch.Tensor:
+        "given_models.py:166-168: InverseSpectrogram -- perfect reconstruction (aa_istft_f32)"
+        return self.match_sizes(self._istft(reps))
 
 
 class MagSpectrogramAE(_StftFrontEnd):
@@ -289,6 +359,10 @@ class MagSpectrogramAE(_StftFrontEnd):
 
     def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
         return self._run(waveform, "power")
+
+    def decode(self, reps: torch.Tensor, **kwargs) -> torch.Tensor:
+        "given_models.py:187-189: GriffinLim *guesses* at the phase (kwargs: n_iter, momentum, rand_init, init_angles)"
+        return self.match_sizes(self._griffinlim(reps, **kwargs))
 
 
 class MagDPhaseSpectrogramAE(_StftFrontEnd):
@@ -314,6 +388,26 @@ class MagDPhaseSpectrogramAE(_StftFrontEnd):
             check(lib.aa_magdphase_ex_f32(ptr(spec), c, f, t, int(bool(self.use_cos)), int(bool(self.debug)), ptr(out), stream_ptr()))
         return out.cpu() if on_cpu else out
 
+    def decode(self, reps: torch.Tensor, **kwargs) -> torch.Tensor:
+        """given_models.py:233-254: split [2c, F, T] into magnitudes and phase differences, integrate the phase along time (wrap at
+        2 pi; first frame per `init`: 'true' | 'rand' | 'zero'), spec = mag * exp(i theta), then InverseSpectrogram.  `cheat`
+        (reuse the encoder's stored phases) is a debugging aid of the reference and is not carried."""
+        if self.cheat:
+            raise NotImplementedError("cheat=True (decode with the phases stored by encode) is a debugging aid and is not supported")
+        if reps.dim() != 3 or reps.shape[0] % 2:
+            raise ValueError("MagDPhaseSpectrogramAE.decode expects [2 * channels, F, T]")
+        on_cpu = not reps.is_cuda
+        dev = _lib.ensure_device(None if on_cpu else reps.device)
+        with torch.cuda.device(dev):
+            r = reps.to(f"cuda:{dev}").float().contiguous()
+            c, f, t = r.shape[0] // 2, r.shape[1], r.shape[2]
+            mode = {"true": 0, "rand": 1}.get(self.init, 2)
+            th0 = torch.rand((c, f), device=r.device) if mode == 1 else None
+            spec = torch.empty((c, f, t), dtype=torch.complex64, device=r.device)
+            check(lib.aa_magdphase_decode_f32(ptr(r), c, f, t, mode, None if th0 is None else ptr(th0), ptr(spec), stream_ptr()))
+            wav = self.match_sizes(self._istft(spec))
+        return wav.cpu() if on_cpu else wav
+
 
 class MelSpectrogramAE(_StftFrontEnd):
     "Mel power spectrogram (given_models.py:257-283): torchaudio MelSpectrogram defaults (128 HTK bins)"
@@ -324,6 +418,38 @@ class MelSpectrogramAE(_StftFrontEnd):
 
     def encode(self, waveform: torch.Tensor, **kwargs) -> torch.Tensor:
         return self._run(waveform, "mel", out=kwargs.get("out"), freq_major=bool(kwargs.get("freq_major", False)))
+
+    def _inv_mel_pinv(self):
+        """T.InverseMelScale(n_stft=n_fft // 2 + 1) as the reference builds it (given_models.py:268): torchaudio DEFAULTS for
+        everything else -- n_mels 128, sample_rate 16000, f_min 0, f_max 8000, HTK -- i.e. NOT the encoder's 48 kHz bank (a
+        reference quirk, kept).  Its forward is relu(lstsq(fb^T, mel)) = relu(pinv(fb^T) mel) for the full-rank underdetermined
+        system; the pseudo-inverse is formed once in float64."""
+        if getattr(self, "_pinv", None) is None:
+            fb = melscale_fbanks(self.n_fft // 2 + 1, 0.0, 8000.0, 128, 16000, None, "htk").double()      # [F, 128]
+            self._pinv = torch.linalg.pinv(fb.T).float().contiguous()                                         # [F, 128]
+        return self._pinv
+
+    def inverse_melscale(self, melspec: torch.Tensor) -> torch.Tensor:
+        "T.InverseMelScale.forward: [..., 128, T] -> [..., n_fft // 2 + 1, T] (aa_inverse_mel_f32)"
+        on_cpu = not melspec.is_cuda
+        dev = _lib.ensure_device(None if on_cpu else melspec.device)
+        with torch.cuda.device(dev):
+            m = melspec.to(f"cuda:{dev}").float()
+            lead, (nm, t) = m.shape[:-2], m.shape[-2:]
+            if nm != 128:
+                raise ValueError(f"Expected an input with 128 mel bins. Found: {nm}")
+            rows = int(math.prod(lead)) if len(lead) else 1
+            m3 = m.reshape(rows, nm, t)
+            f = self.n_fft // 2 + 1
+            out = torch.empty((rows, f, t), dtype=torch.float32, device=m.device)
+            P = self._inv_mel_pinv().to(m.device)
+            check(lib.aa_inverse_mel_f32(ptr(P), ptr(m3), rows, nm, f, t, m3.stride(0), m3.stride(1), m3.stride(2), ptr(out), stream_ptr()))
+            out = out.reshape(*lead, f, t)
+        return out.cpu() if on_cpu else out
+
+    def decode(self, melspec: torch.Tensor, **kwargs) -> torch.Tensor:
+        "given_models.py:278-280: InverseMelScale then GriffinLim"
+        return self.match_sizes(self._griffinlim(self.inverse_melscale(melspec), **kwargs))
 
 
 class DVAEWrapper(GivenModelClass):

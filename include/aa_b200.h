@@ -277,6 +277,34 @@ int aa_projector_half_bwd_f32(const float* const* w_host, const float* const* b_
                               float* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Decoder side of the STFT given models (round-trip demos).
+ * aa_istft_f32 replaces T.InverseSpectrogram / torch.istft (given_models.py:159,168): spec = complex64
+ * (interleaved re, im) addressed as spec[row*row_stride + f*stride_f + t*stride_t] (strides in complex
+ * elements: both torch.stft's [T][F]-memory view and a contiguous [F][T] tensor work); window = device
+ * pointer to n_fft floats or NULL (periodic Hann); out [rows][out_len], out_len <= hop*(n_frames-1) for
+ * center != 0 (torch's length=None); workspace >= aa_istft_workspace_floats floats.  Deterministic
+ * (gather overlap-add, no float atomics).
+ * aa_griffinlim_update_c64: one iteration's phase update of torchaudio.functional.griffinlim
+ * (given_models.py:181,189,269): angles = rebuilt - momentum*tprev (skipped when first != 0),
+ * angles /= |angles| + 1e-16, tprev <- rebuilt, prod = mag * angles; n complex elements, momentum already
+ * divided by (1 + momentum).
+ * aa_inverse_mel_f32 replaces T.InverseMelScale (given_models.py:268,279): out [rows][n_freq][n_frames] =
+ * relu(pinv [n_freq][n_mels] x mel), mel addressed by (row, mel, frame) strides in elements.
+ * ------------------------------------------------------------------------------------------ */
+int64_t aa_istft_workspace_floats(int64_t rows, int n_fft, int64_t n_frames);
+int aa_istft_f32(const void* spec, int64_t rows, int n_fft, int hop, int center, int64_t n_frames, int64_t row_stride,
+                 int64_t stride_f, int64_t stride_t, const float* window, float* out, int64_t out_len, float* workspace,
+                 void* stream);
+int aa_griffinlim_update_c64(const void* rebuilt, void* tprev, const float* mag, void* prod, int64_t n, float momentum, int first,
+                             void* stream);
+/* MagDPhaseSpectrogramAE.decode (given_models.py:233-254): reps [2c][f][t] (magnitudes, then phase differences) -> complex64
+ * spec [c][f][t] = mag * exp(i theta), theta integrated along time with the reference's 2 pi wrap; init_mode 0 = 'true'
+ * (theta_0 = dtheta_0), 1 = 'rand' (theta_0 from theta0 [c][f]), 2 = 'zero'.  Feed spec to aa_istft_f32. */
+int aa_magdphase_decode_f32(const float* reps, int64_t c, int64_t f, int64_t t, int init_mode, const float* theta0, void* spec, void* stream);
+int aa_inverse_mel_f32(const float* pinv, const float* mel, int64_t rows, int n_mels, int n_freq, int64_t n_frames, int64_t mel_row_stride,
+                       int64_t mel_stride_m, int64_t mel_stride_t, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused loss entry points of the two training steps: one call evaluates every loss term
  * and one call writes every gradient; the per-term kernels above run back to back on `stream` and
  * accumulate straight into the gradient buffers.  Replaces train_aa_mixer_accel.py:504-517 (mixer) and

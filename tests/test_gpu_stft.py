@@ -344,3 +344,65 @@ def test_v3_kernel_n1024_two_frames_per_item(aab, monkeypatch, hop, n, rows):
         ycx = aab.SpectrogramAE(n_fft=1024, hop_length=hop).encode(x.cuda())
         assert rel_l2(yp, refp) < 1e-5, f"power, AA_STFT_V3={v3}"
         assert rel_l2(ycx.abs() ** 2, yp) < 1e-5
+
+
+# ---------------------------------------------------------------- decoders
+@pytest.mark.parametrize("tag,n_fft,hop", [("1024_256", 1024, 256), ("2048_512", 2048, 512)])
+def test_decoders_match_the_reference_decoders(golden, tag, n_fft, hop):
+    """SpectrogramAE.decode (aa_istft_f32), MagSpectrogramAE.decode / MelSpectrogramAE.decode (GriffinLim on the CUDA STFT and
+    inverse-STFT kernels, aa_griffinlim_update_c64, aa_inverse_mel_f32) against outputs of the reference's own decoders
+    (tests/golden/decoders.npz); GriffinLim with the reproducible start (ones) and 8 iterations as in the fixture."""
+    import audio_algebra_b200 as aab
+    g = golden("decoders")
+    x = torch.from_numpy(g["x"]).cuda()
+    m = aab.SpectrogramAE(n_fft=n_fft, hop_length=hop)
+    z = torch.from_numpy(g[f"rand_spec_{tag}"]).cuda()
+    assert rel_l2(m._istft(z), g[f"rand_istft_{tag}"]) < 5e-6                       # contiguous [F][T] input
+    spec = m.encode(x)                                                               # torch.stft's own (transposed-view) layout
+    rec = m.decode(spec)
+    assert rec.shape == x.shape and rel_l2(rec, g[f"roundtrip_{tag}"]) < 5e-6 and rel_l2(rec, x) < 5e-6
+    reps, recons = m(x)                                                              # GivenModelClass.forward -> (reps, recons)
+    assert rel_l2(recons, x) < 5e-6
+    mm = aab.MagSpectrogramAE(n_fft=n_fft, hop_length=hop)
+    p = mm.encode(x)
+    gl = mm.decode(p, rand_init=False, n_iter=8)
+    assert gl.shape == x.shape and rel_l2(gl, g[f"gl8_{tag}"]) < 2e-4
+    me = aab.MelSpectrogramAE(sample_rate=48000, n_fft=n_fft, hop_length=hop)
+    mel = me.encode(x)
+    inv = me.inverse_melscale(mel)
+    assert rel_l2(inv, g[f"invmel_{tag}"]) < 5e-5
+    assert rel_l2(me.decode(mel, rand_init=False, n_iter=8), g[f"mel_gl8_{tag}"]) < 2e-2
+
+
+def test_griffinlim_default_random_start_reduces_the_spectral_error():
+    "T.GriffinLim defaults (random phase start, 32 iterations, momentum 0.99): the rebuilt magnitude approaches the given one"
+    import audio_algebra_b200 as aab
+    torch.manual_seed(0)
+    t = torch.arange(16384, device="cuda") / 48000.0
+    x = (0.5 * torch.sin(2 * torch.pi * 440.0 * t) + 0.25 * torch.sin(2 * torch.pi * 1234.0 * t))[None, None].repeat(2, 2, 1)
+    mm = aab.MagSpectrogramAE(n_fft=1024, hop_length=256)
+    p = mm.encode(x)
+    errs = []
+    for n_iter in (1, 32):
+        torch.manual_seed(1)
+        w = mm.decode(p, n_iter=n_iter)
+        assert w.shape == x.shape
+        errs.append(float((mm.encode(w).sqrt() - p.sqrt()).norm() / p.sqrt().norm()))
+    assert errs[1] < 0.5 * errs[0] and errs[1] < 0.2, errs
+
+
+def test_magdphase_decode_matches_the_reference(golden):
+    "MagDPhaseSpectrogramAE.decode (aa_magdphase_decode_f32 + aa_istft_f32) against the reference's own output; round trip; init variants run"
+    import audio_algebra_b200 as aab
+    g = golden("decoders")
+    reps = torch.from_numpy(g["mdp_reps"]).cuda()
+    md = aab.MagDPhaseSpectrogramAE(n_fft=1024, hop_length=256)
+    x0 = torch.from_numpy(g["x"][0]).cuda()
+    md.encode(x0)   # sets orig_shape for match_sizes (the encode parity has its own test: phases wrap, so it is not compared elementwise here)
+    rec = md.decode(reps)
+    assert rec.shape == x0.shape and rel_l2(rec, g["mdp_decode"]) < 2e-4 and rel_l2(rec, x0) < 2e-4
+    for init in ("zero", "rand"):
+        w = aab.MagDPhaseSpectrogramAE(n_fft=1024, hop_length=256, init=init)
+        w.encode(x0)
+        out = w.decode(reps)
+        assert out.shape == x0.shape and bool(torch.isfinite(out).all())
