@@ -434,6 +434,8 @@ class MelSpectrogramAE(_StftFrontEnd):
         on_cpu = not melspec.is_cuda
         dev = _lib.ensure_device(None if on_cpu else melspec.device)
         with torch.cuda.device(dev):
+            if melspec.dim() < 2:
+                raise ValueError(f"expected a mel spectrogram [..., 128, time], got shape {tuple(melspec.shape)}")
             m = melspec.to(f"cuda:{dev}").float()
             lead, (nm, t) = m.shape[:-2], m.shape[-2:]
             if nm != 128:

@@ -163,8 +163,10 @@ def test_empty_batch_and_errors(aab):
         m.encode(torch.zeros(1, 2, 512, device="cuda"))  # reflect pad needs > n_fft/2 samples
     with pytest.raises(AaError):
         aab.SpectrogramAE(n_fft=1000)  # not a power of two
+    with pytest.raises(ValueError):
+        m.decode(torch.zeros(1))   # needs [..., 128, T]
     with pytest.raises(NotImplementedError):
-        m.decode(torch.zeros(1))
+        aab.DVAEWrapper(debug=False).decode(torch.zeros(1, 64, 8))   # the diffusion sampler is out of scope
 
 
 def test_full_size_properties(aab):
