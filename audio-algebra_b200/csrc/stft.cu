@@ -1113,8 +1113,8 @@ static int v3_build_tables(AaStftPlan* p) {
   for (int l = 0; l < 32; ++l) {
     for (int e = 0; e < 2; ++e) {
       const double phi = 2.0 * PI * (double)(2 * l + e) / (double)nf;
-      lc[4 * l + 2 * e] = (float)std::cos(phi);
-      lc[4 * l + 2 * e + 1] = (float)std::sin(phi);
+      lc[4 * l + e] = (float)std::cos(phi);         // (cos phi0, cos phi1, sin phi0, sin phi1): packed pairs for the window FFMA2s
+      lc[4 * l + 2 + e] = (float)std::sin(phi);
     }
     const int k1 = l % r1;
     lc[128 + 2 * l] = (float)std::cos(2.0 * PI * k1 / (double)nf);

@@ -40,7 +40,7 @@ struct Stft3Args {
   int n_items, items_per_pair;   // row pairs x ceil(frames / FR)
   int n_freq, n_mels, wav_ok8, wav_ok16, prefetch;
   const float2* tw1;         // NF = 2048: [32][32] W_1024^(k1 n2);  NF = 1024: [16][32] W_512^(k1 n2)
-  const float* lane_consts;  // float4[32] Hann phases (cos, sin of 2 pi (2 lane + {0,1}) / NF) + float2[32] W_NF^(k1 of the lane)
+  const float* lane_consts;  // float4[32] Hann phases (cos phi0, cos phi1, sin phi0, sin phi1; phi_e = 2 pi (2 lane + e) / NF) + float2[32] W_NF^(k1 of the lane)
   const unsigned char* mel_tab;   // kV3MelTab bytes (see above), then uint32 [n_mels]: run slot of L | run slot of H << 16
 };
 
@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft_v3_kernel(const __grid_cons
     float2 re[32], im[32];
     {
       // Hann window of sample 2 (32 n1 + lane) + e: 0.5 - 0.5 cos(2 pi n1 / R1 + phi_e), phi_e = 2 pi (2 lane + e) / NF
-      const float4 ph = s_lane[lane];   // (cos phi0, sin phi0, cos phi1, sin phi1)
+      const float4 ph = s_lane[lane];   // (cos phi0, cos phi1, sin phi0, sin phi1)
+      const float2 phc = make_float2(ph.x, ph.y), phs = make_float2(ph.z, ph.w);
       if (fast) {
         float2 xa[32], xb[32];
 #pragma unroll
@@ -204,8 +205,9 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft_v3_kernel(const __grid_cons
 #pragma unroll
         for (int s1 = 0; s1 < R1; ++s1) {
           const int n1 = FR == 1 ? bitrev5(s1) : bitrev4(s1);
-          const float w0 = fmaf(0.5f * aa_consts::kSin32[FR * n1], ph.y, fmaf(-0.5f * aa_consts::kCos32[FR * n1], ph.x, 0.5f));
-          const float w1 = fmaf(0.5f * aa_consts::kSin32[FR * n1], ph.w, fmaf(-0.5f * aa_consts::kCos32[FR * n1], ph.z, 0.5f));
+          // both window values of the lane's sample pair in one packed FFMA chain (same fmaf arithmetic per component)
+          const float2 w01 = pfma(phs, 0.5f * aa_consts::kSin32[FR * n1], pfma(phc, -0.5f * aa_consts::kCos32[FR * n1], make_float2(0.5f, 0.5f)));
+          const float w0 = w01.x, w1 = w01.y;
 #pragma unroll
           for (int f = 0; f < FR; ++f) {
             re[f * R1 + s1] = make_float2(xa[f * R1 + s1].x * w0, xb[f * R1 + s1].x * w0);
@@ -235,8 +237,8 @@ __global__ void __launch_bounds__(kV3W * 32, 1) stft_v3_kernel(const __grid_cons
             const int n1 = FR == 1 ? half * 16 + q : q;
             const int sl = FR == 1 ? bitrev5(n1) : half * 16 + bitrev4(q);
             const float2 xa = FA[32 * q + lane], xb = FB[32 * q + lane];
-            const float w0 = fmaf(0.5f * aa_consts::kSin32[FR * n1], ph.y, fmaf(-0.5f * aa_consts::kCos32[FR * n1], ph.x, 0.5f));
-            const float w1 = fmaf(0.5f * aa_consts::kSin32[FR * n1], ph.w, fmaf(-0.5f * aa_consts::kCos32[FR * n1], ph.z, 0.5f));
+            const float2 w01 = pfma(phs, 0.5f * aa_consts::kSin32[FR * n1], pfma(phc, -0.5f * aa_consts::kCos32[FR * n1], make_float2(0.5f, 0.5f)));
+            const float w0 = w01.x, w1 = w01.y;
             re[sl] = make_float2(xa.x * w0, xb.x * w0);
             im[sl] = make_float2(xa.y * w1, xb.y * w1);
           }
