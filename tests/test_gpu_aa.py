@@ -469,3 +469,39 @@ def test_projector_forward_tensor_core_path_is_fp32_accurate(aab):
     (zo.square().mean() + yro.square().mean()).backward()
     assert rel_l2(yc.grad, yd.grad) < 1e-4
     assert rel_l2(aa.encoder[0].lin.weight.grad, P[0].grad) < 1e-4
+
+
+def test_projector_backward_cabi_flags(aab):
+    "aa_projector_half_bwd_f32 on the tcgen05 path: gscale, accumulate_gx / accumulate_gw, and gx = NULL behave as the header says"
+    from audio_algebra_b200._lib import lib, check, ptr, stream_ptr
+    from audio_algebra_b200.aa_mixer import _ptr_array
+    torch.manual_seed(5)
+    aa = aab.AudioAlgebra(64, 64).cuda()
+    ws = [blk.lin.weight.detach().contiguous() for blk in aa.encoder]
+    bs = [blk.lin.bias.detach().contiguous() for blk in aa.encoder]
+    wp, k1 = _ptr_array(ws)
+    bp, k2 = _ptr_array(bs)
+    b, t = 6, 300
+    x, gout = torch.randn(b, 64, t, device="cuda"), torch.randn(b, 64, t, device="cuda")
+    wsb = torch.empty(int(lib.aa_projector_bwd_workspace_floats()), device="cuda")
+
+    def run(gx, gws, gbs, acc_gx, acc_gw, gscale):
+        gwp, k3 = _ptr_array(gws)
+        gbp, k4 = _ptr_array(gbs)
+        check(lib.aa_projector_half_bwd_f32(wp, bp, 64, 64, 1, ptr(x), ptr(gout), b, t, None if gx is None else ptr(gx), acc_gx, gwp, gbp, acc_gw,
+                                            gscale, ptr(wsb), stream_ptr()))
+        torch.cuda.synchronize()
+
+    gx0 = torch.empty_like(x)
+    gw0, gb0 = [torch.empty_like(w) for w in ws], [torch.empty_like(v) for v in bs]
+    run(gx0, gw0, gb0, 0, 0, 1.0)
+    gx1 = torch.full_like(x, 0.25)
+    gw1, gb1 = [torch.full_like(w, -1.5) for w in ws], [torch.full_like(v, 2.0) for v in bs]
+    run(gx1, gw1, gb1, 1, 1, 0.5)
+    assert rel_l2(gx1, gx0 + 0.25) < 1e-6            # gscale applies to the parameter gradients only
+    for i in range(4):
+        assert rel_l2(gw1[i], 0.5 * gw0[i] - 1.5) < 1e-6 and rel_l2(gb1[i], 0.5 * gb0[i] + 2.0) < 1e-6
+    gw2, gb2 = [torch.empty_like(w) for w in ws], [torch.empty_like(v) for v in bs]
+    run(None, gw2, gb2, 0, 0, 1.0)
+    for i in range(4):
+        assert torch.equal(gw2[i], gw0[i]) and torch.equal(gb2[i], gb0[i])   # deterministic, and independent of gx
