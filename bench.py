@@ -235,6 +235,40 @@ def run_extras(dev):
         arch = aab.aa_effects.do_mixing(batch, dvb.model, aa2, dev)
         aab.aa_effects.effects_losses(arch)["loss"].backward()
 
+    # ---- round-2 tensor-core contractions of the training step at its sizes (B = 512, [64, 512] latents) ----
+    zt = torch.randn(512, 64, 512, generator=g, device=dev)
+    gt = torch.randn(512, 64, 512, generator=g, device=dev)
+    aa3 = aab.AudioAlgebra(64, 64).cuda()
+    yv = zt.clone().requires_grad_(True)
+    fwd_ms = timed(lambda: aa3.encode(zt), 5)
+
+    def proj_fb():
+        yv.grad = None
+        for p_ in aa3.parameters():
+            p_.grad = None
+        (aa3.encode(yv) * gt).sum().backward()
+
+    fb_ms = timed(proj_fb, 5)
+    out["projector_half"] = {"fwd_ms": fwd_ms, "fwd_plus_bwd_ms": fb_ms, "tokens": 512 * 512,
+                             "note": "one projector half (4 EmbedBlocks) on [512,64,512]: proj_fwd_tc_kernel (3xTF32) / proj_bwd_tc_kernel (bf16x3), "
+                                     "fwd+bwd includes the elementwise product and sum of the test loss"}
+    zc = zt.clone().requires_grad_(True)
+
+    def cov_fb():
+        zc.grad = None
+        aab.vicreg_cov_loss(zc).backward()
+
+    out["vicreg_cov"] = {"fwd_ms": timed(lambda: aab.vicreg_cov_loss(zt), 5), "fwd_plus_bwd_ms": timed(cov_fb, 5), "b": 512, "d": 32768,
+                         "note": "Gram identity on tcgen05: gram_bb_tc_kernel + cov_bwd_tc_kernel (3-term TF32 split, MN-major Xc operand)"}
+    del zt, gt, yv, zc
+    # ---- decoder round trip: SpectrogramAE x -> encode -> decode on 64 chunks ----
+    xr = synth(64, 77, dev)
+    sp = aab.SpectrogramAE(n_fft=N_FFT, hop_length=HOP)
+    rr = {}
+    rt_ms = timed(lambda: rr.__setitem__("o", sp.decode(sp.encode(xr))), 3, warm=1)
+    out["spectrogram_roundtrip"] = {"ms": rt_ms, "chunks": 64, "rel_l2_error": float((rr["o"] - xr).norm() / xr.norm()),
+                                    "note": "SpectrogramAE.encode -> decode (aa_istft_f32): the reference's 'perfect reconstruction' decoder"}
+    del xr, rr
     ms = timed(effects_step, 3, warm=1)
     out["effects_step"] = {"ms": ms, "batch": Be, "chunk_samples": Nm, "audio_s_per_s": 4 * Be * Nm / SR / (ms * 1e-3),
                            "note": "train_aa_effects step: a1,b1,a2,b2 encoded as one 4B batch, projector enc/dec, effect guesses, 4 loss terms, backward"}
