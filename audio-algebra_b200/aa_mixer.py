@@ -78,15 +78,22 @@ def _ws(n, device):
 def latent_lincomb(zs, coeffs, out=None) -> Tensor:
     "sum_j coeffs[j] * zs[j] in one pass (zsum, effect guesses zb2 - zb1 + za1, z + diff, ...)"
     zs = [_f32c(z) for z in zs]
-    assert 1 <= len(zs) <= 8 and len(zs) == len(coeffs)
+    assert len(zs) >= 1 and len(zs) == len(coeffs)
     n = zs[0].numel()
     assert all(z.numel() == n for z in zs)
     if out is None:
         out = torch.empty_like(zs[0])
-    pa, keep = _ptr_array(zs)
-    ca = (C.c_float * len(zs))(*[float(c) for c in coeffs])
+    cs = [float(c) for c in coeffs]
     with torch.cuda.device(zs[0].device):
-        check(lib.aa_latent_lincomb_f32(len(zs), pa, ca, ptr(out), n, stream_ptr()))
+        first = True
+        while zs:   # the kernel takes up to 8 terms per pass; more stems (the reference allows any maxstems) accumulate into `out`
+            take = 8 if first else 7
+            terms, tc = (zs[:take], cs[:take]) if first else ([out] + zs[:take], [1.0] + cs[:take])
+            zs, cs = zs[take:], cs[take:]
+            pa, keep = _ptr_array(terms)
+            ca = (C.c_float * len(terms))(*tc)
+            check(lib.aa_latent_lincomb_f32(len(terms), pa, ca, ptr(out), n, stream_ptr()))
+            first = False
     return out
 
 
@@ -514,7 +521,9 @@ def get_stems_faders(batch, dl_iter, dl, maxstems=2, unity_gain=False, debug=Fal
         if debug:
             print("  next_stem.shape = ", next_stem.shape)
         stems.append(next_stem)
-    return stems, faders.to(device), dl_iter
+    fdev = faders.to(device)
+    fdev._aa_host = faders.tolist()   # read by do_mixing instead of a device -> host copy of the same numbers
+    return stems, fdev, dl_iter
 
 
 class _LazyArchive(dict):
@@ -546,7 +555,8 @@ def do_mixing(stems, faders, given_model, aa_model, device, debug=False, **kwarg
     (identical zmix / archive['ymix']).  Given models that expose `encode_mix` (the conv encoder) take the fader scaling and the
     stem sum inside their first layer's load, so `fadedstem` / `mix` are not written to HBM unless the archive entry is read."""
     zs, ys, yrecons = [], [], []
-    fl = [float(f) for f in (faders.detach().cpu().tolist() if torch.is_tensor(faders) else faders)]
+    host = getattr(faders, "_aa_host", None)   # get_stems_faders keeps the host copy it drew the faders from: no device sync here
+    fl = [float(f) for f in (host if host is not None else (faders.detach().cpu().tolist() if torch.is_tensor(faders) else faders))]
     stems = [s.to(device) for s in stems]
     fused = hasattr(given_model, "encode_mix") and len(stems) <= 4
     fadedstems = None if fused else []

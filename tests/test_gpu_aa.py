@@ -505,3 +505,16 @@ def test_projector_backward_cabi_flags(aab):
     run(None, gw2, gb2, 0, 0, 1.0)
     for i in range(4):
         assert torch.equal(gw2[i], gw0[i]) and torch.equal(gb2[i], gb0[i])   # deterministic, and independent of gx
+
+
+def test_lincomb_more_than_eight_terms_and_host_faders(aab):
+    "latent_lincomb chunks beyond 8 terms (the reference allows any maxstems); get_stems_faders hands do_mixing its host copy of the faders"
+    g = torch.Generator().manual_seed(8)
+    zs = [torch.randn(3, 64, 40, generator=g) for _ in range(19)]
+    cs = [float(c) for c in torch.randn(19, generator=g)]
+    ref = sum(c * z.double() for c, z in zip(cs, zs))
+    assert rel_l2(aab.latent_lincomb([z.cuda() for z in zs], cs), ref) < 1e-6
+    batch = torch.rand(4, 2, 1024, device="cuda")
+    dl = [torch.rand(4, 2, 1024) for _ in range(3)]
+    stems, faders, it = aab.get_stems_faders(batch, iter(dl), dl, maxstems=3)
+    assert faders.is_cuda and faders._aa_host == faders.cpu().tolist()
