@@ -813,6 +813,7 @@ struct TcState {
   bool fuse_ru128 = false;
   int ru_ctas_per_sm[2] = {1, 1};
   int bn_1x1_wide = 0;
+  int nepi_k7_128 = 0, nacc_min = 0;
   int res_tma = 1;             // ResidualUnit 1x1 layers: residual / result tiles through TMA (AA_RES_TMA=0: per-thread loads, staged stores)
 };
 
@@ -881,6 +882,8 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   st->ru_ctas_per_sm[0] = std::max(st->ru_ctas_per_sm[0], getenv("AA_RU_CTAS32") ? atoi(getenv("AA_RU_CTAS32")) : 2);
   if (getenv("AA_RES_TMA")) st->res_tma = atoi(getenv("AA_RES_TMA"));
   if (getenv("AA_1X1_BN256")) st->bn_1x1_wide = atoi(getenv("AA_1X1_BN256"));
+  if (getenv("AA_TC_NEPI128")) st->nepi_k7_128 = atoi(getenv("AA_TC_NEPI128"));
+  if (getenv("AA_TC_NACC")) st->nacc_min = atoi(getenv("AA_TC_NACC"));
   if (getenv("AA_DEBUG")) fprintf(stderr, "[aa] ru_fused CTAs/SM: C=32 -> %d, C=64 -> %d\n", st->ru_ctas_per_sm[0], st->ru_ctas_per_sm[1]);
   *out = st;
   return AA_OK;
@@ -1060,7 +1063,11 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     a.elu = ly.elu; a.tanh_out = (last && apply_tanh) ? 1 : 0;
     const int stage_bytes = BM * p.bk * 2 + ((bn * p.bk * 2 + 1023) & ~1023);
     a.n_epi = last ? 1 : (bn <= 64 ? 4 : (bn <= 128 ? (n_chunks_total <= 8 ? 3 : 2) : 1));
+    // (dev knob AA_TC_NEPI128, measured on the C = 128 k7 layers: 1 group / 5 stages 124 us, 2 groups / 4 stages 120 us (default),
+    //  3 groups / 3 stages 135 us: the layer is not bound by the depth of the operand ring)
+    if (st->nepi_k7_128 > 0 && !last && bn == 128 && n_chunks_total > 8) a.n_epi = st->nepi_k7_128;
     a.n_acc = std::min(kMaxAcc, std::min(512 / bn, 2 * a.n_epi));
+    if (st->nacc_min > 0) a.n_acc = std::max(a.n_acc, std::min(512 / bn, st->nacc_min));
     // ResidualUnit 1x1 layers with 64-channel boxes: residual in / result out through TMA, in place in one swizzled tile buffer per group
     // (measured per layer at B = 64: C = 128 95 -> 67 us, C = 256 98 -> 79 us; C = 512 -- 8 K chunks, bound by re-streaming the
     //  weights from L2 for every tile -- 110 -> 120 us: those layers keep the per-thread path unless AA_RES_TMA=2)
