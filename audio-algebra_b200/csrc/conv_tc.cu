@@ -460,6 +460,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
   }
 }
 
+#include "conv_cg2.cuh"
+
 // ---- layer 0: fp32 stems [B][cin<=4][N] (fader-scaled sum) -> conv k (<=7), cout <= 32 -> ELU -> bf16 [B][N][cout] ----
 struct L0Args {
   const float* x[4];
@@ -814,6 +816,7 @@ struct TcState {
   int ru_ctas_per_sm[2] = {1, 1};
   int bn_1x1_wide = 0;
   int nepi_k7_128 = 0, nacc_min = 0;
+  int cg2 = 1;                 // wide non-residual layers as cta_group::2 MMAs on CTA pairs (conv_cg2.cuh; AA_TC_CG2=0: one CTA per tile)
   int res_tma = 1;             // ResidualUnit 1x1 layers: residual / result tiles through TMA (AA_RES_TMA=0: per-thread loads, staged stores)
 };
 
@@ -862,6 +865,7 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_c32k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
@@ -884,6 +888,7 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   if (getenv("AA_1X1_BN256")) st->bn_1x1_wide = atoi(getenv("AA_1X1_BN256"));
   if (getenv("AA_TC_NEPI128")) st->nepi_k7_128 = atoi(getenv("AA_TC_NEPI128"));
   if (getenv("AA_TC_NACC")) st->nacc_min = atoi(getenv("AA_TC_NACC"));
+  if (getenv("AA_TC_CG2")) st->cg2 = atoi(getenv("AA_TC_CG2"));
   if (getenv("AA_DEBUG")) fprintf(stderr, "[aa] ru_fused CTAs/SM: C=32 -> %d, C=64 -> %d\n", st->ru_ctas_per_sm[0], st->ru_ctas_per_sm[1]);
   *out = st;
   return AA_OK;
@@ -1093,6 +1098,36 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     const int threads = 64 + 128 * a.n_epi;
     AA_REQUIRE(last || ly.elu, "bf16 layers without ELU are not supported on the tensor-core path (layer %zu)", i);
     const bool res = a.res != nullptr;
+    if (st->cg2 && !res && !last && p.bk == 64 && bn == kCg2BN && ly.cout % kCg2BN == 0 && a.m_tiles >= 2 && aa::num_sms() >= 2) {
+      // wide non-residual layer: CTA pairs, M = 256 cta_group::2 MMAs, each CTA loads half of the weight box (conv_cg2.cuh)
+      CUtensorMap tmBh;
+      cuuint64_t dims[2] = {(cuuint64_t)p.k_total, (cuuint64_t)ly.cout};
+      cuuint64_t strides[1] = {(cuuint64_t)p.k_total * 2};
+      cuuint32_t box[2] = {(cuuint32_t)p.bk, (cuuint32_t)(kCg2BN / 2)};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = encode(&tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.w2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B half) failed for layer %zu: %d", i, (int)r);
+      const int stage2 = BM * 64 * 2 + (kCg2BN / 2) * 64 * 2;
+      const int fixed = 1024 + 512 + BM * (kCg2BN * 2 + 16) + kCg2BN * 4 + 256;
+      a.stages = std::max(2, std::min(8, (st->max_smem - fixed) / stage2));
+      const int smem2 = a.stages * stage2 + fixed;
+      const long long units = batch * ((a.m_tiles + 1) / 2) * a.n_tiles_n;
+      const int grid2 = (int)std::min<long long>(2 * units, (long long)(aa::num_sms() & ~1));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3((unsigned)kCg2Threads); cfg.dynamicSmemBytes = (size_t)smem2; cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, tmA, tmBh, a);
+      AA_REQUIRE(le == cudaSuccess, "conv_tc2_kernel launch failed for layer %zu: %s", i, cudaGetErrorString(le));
+      AA_LAUNCH_CHECK();
+      if (ly.role == ROLE_RES_SECOND) res_buf = -1;
+      cur = dst;
+      l = lout;
+      continue;
+    }
     if (p.bk == 64) {
       if (res) conv_tc_kernel<64, true><<<grid, threads, smem, stream>>>(tmA, tmB, tmR, tmO, a);
       else conv_tc_kernel<64, false><<<grid, threads, smem, stream>>>(tmA, tmB, tmR, tmO, a);

@@ -510,3 +510,28 @@ def test_encode_on_two_streams_does_not_share_activations(setup):
             outs["b"] = dv.encode(xb)
     torch.cuda.synchronize()
     assert torch.equal(outs["a"], ya) and torch.equal(outs["b"], yb)
+
+
+def test_cta_pair_layers_are_bit_identical_to_the_single_cta_kernel(setup):
+    """conv_tc2_kernel (2-CTA clusters, tcgen05.mma.cta_group::2 with M = 256, each CTA loading half of the weight box) against
+    conv_tc_kernel (AA_TC_CG2=0 at handle creation) on the wide layers: the same products accumulated in the same K order, so the
+    embeddings must agree bit for bit -- incl. odd row-tile counts (ghost tile of the pair) and ragged lengths."""
+    import os
+    aab, O, enc_o, dv = setup
+
+    def make(cg2):
+        os.environ["AA_TC_CG2"] = "1" if cg2 else "0"
+        try:
+            w = aab.DVAEWrapper(debug=False, compute_dtype="bf16")
+            w.model.load_oracle_weights(enc_o)
+            w = w.cuda()
+            w.encode(torch.zeros(1, 2, 1024, device="cuda"))   # the handle reads the switch at its first bf16 forward
+        finally:
+            os.environ.pop("AA_TC_CG2", None)
+        return w
+
+    pair, single = make(True), make(False)
+    for shape, seed in [((4, 2, 131072), 41), ((3, 2, 128 * 128 * 3), 42), ((2, 2, 50000), 43), ((1, 2, 4096 * 5 + 77), 44), ((7, 2, 16384), 45)]:
+        x = _x(shape, seed).cuda()
+        a, b = pair.encode(x), single.encode(x)
+        assert torch.equal(a, b), (shape, float((a - b).abs().max()))
