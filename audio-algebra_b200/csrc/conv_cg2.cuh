@@ -61,8 +61,8 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
 }
 
 constexpr int kCg2Threads = 64 + 128;   // TMA warp, MMA warp, one epilogue group
-constexpr int kCg2BN = 256;
 
+template <int kCg2BN>   // N of the pair's tile: 256 (C >= 256 layers) or 128 (the C = 128 k7 layers)
 __global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                                                                   const TcArgs a) {
   constexpr int BK = 64;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
   }
   if (warp == 1) {   // both CTAs of the pair allocate together (same warp id, same destination offset)
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * kCg2BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_c
       if (lane == 0) mbar_arrive_cluster(acc ? tempty1 : tempty0);   // the leader may reuse the accumulator once all 8 warps arrived
       asm volatile("bar.sync 1, 128;" ::: "memory");      // tile complete in staging
       for (int idx = et; idx < BM * (kCg2BN / 8); idx += 128) {
-        const int rr = idx >> 5, cv = idx & 31;
+        const int rr = idx / (kCg2BN / 8), cv = idx % (kCg2BN / 8);
         if (m0 + rr < a.lpad) {
           uint4 v;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
@@ -224,6 +224,6 @@ __global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_c
   cluster_sync_all();   // nobody leaves while the pair may still read its shared memory / signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * kCg2BN)) : "memory");
   }
 }

@@ -865,7 +865,8 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
-  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_c32k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
@@ -1098,7 +1099,9 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     const int threads = 64 + 128 * a.n_epi;
     AA_REQUIRE(last || ly.elu, "bf16 layers without ELU are not supported on the tensor-core path (layer %zu)", i);
     const bool res = a.res != nullptr;
-    if (st->cg2 && !res && !last && p.bk == 64 && bn == kCg2BN && ly.cout % kCg2BN == 0 && a.m_tiles >= 2 && aa::num_sms() >= 2) {
+    // (bn = 128 pairs -- AA_TC_CG2=2 -- measured SLOWER: C = 128 k7 120 -> 133 us, 64 -> 128 down-conv 102 -> 110 us; off)
+    if (st->cg2 && !res && !last && p.bk == 64 && (bn == 256 || (bn == 128 && st->cg2 > 1)) && ly.cout % bn == 0 && a.m_tiles >= 2 && aa::num_sms() >= 2) {
+      const int kCg2BN = bn;
       // wide non-residual layer: CTA pairs, M = 256 cta_group::2 MMAs, each CTA loads half of the weight box (conv_cg2.cuh)
       CUtensorMap tmBh;
       cuuint64_t dims[2] = {(cuuint64_t)p.k_total, (cuuint64_t)ly.cout};
@@ -1120,7 +1123,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, tmA, tmBh, a);
+      cudaError_t le = bn == 256 ? cudaLaunchKernelEx(&cfg, conv_tc2_kernel<256>, tmA, tmBh, a) : cudaLaunchKernelEx(&cfg, conv_tc2_kernel<128>, tmA, tmBh, a);
       AA_REQUIRE(le == cudaSuccess, "conv_tc2_kernel launch failed for layer %zu: %s", i, cudaGetErrorString(le));
       AA_LAUNCH_CHECK();
       if (ly.role == ROLE_RES_SECOND) res_buf = -1;
