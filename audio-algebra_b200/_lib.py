@@ -5,7 +5,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaa_b200.so")
+LIB_PATH = os.environ.get("AA_B200_LIB") or os.path.join(_HERE, "libaa_b200.so")   # AA_B200_LIB: dev override (variant builds)
 
 
 class AaError(RuntimeError):

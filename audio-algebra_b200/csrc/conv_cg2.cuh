@@ -60,11 +60,47 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 
-constexpr int kCg2Threads = 64 + 128;   // TMA warp, MMA warp, one epilogue group
+// tcgen05.ld without the wait, and the wait tied to the destination registers (so that no use can be scheduled above it):
+// several loads in flight before one wait
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
-template <int kCg2BN>   // N of the pair's tile: 256 (C >= 256 layers) or 128 (the C = 128 k7 layers)
-__global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-                                                                  const TcArgs a) {
+constexpr int kCg2Threads = 64 + 128;   // TMA warp, MMA warp, one epilogue group
+constexpr int kCg2ResGroups = 4;           // RES: four epilogue groups, each owns a quarter of the tile's columns
+constexpr int kCg2ResThreads = 64 + 128 * kCg2ResGroups;
+
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {   // box -> L2 only
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// RES = true: the ResidualUnit 1x1 layers at C >= 256 (K = C is short, so one CTA per 128 x 128 tile re-streams 2 x 16 KB per 257
+// clocks of MMAs -- twice what the SM can ingest; a pair at N = 256 brings 32 KB per 512 clocks).  Four epilogue groups per CTA split
+// the tile's COLUMNS (all drain the same accumulator: an epilogue warp alone on its scheduler is latency bound -- ~10 k clocks per
+// 128 x 128 tile -- so the per-tile epilogue time falls with the number of groups and comes under the short K loop); the
+// residual tile comes in and the result leaves through TMA, in place in the group's SWIZZLE_128B buffer, as in conv_tc_kernel.
+template <int kCg2BN, bool RES>   // N of the pair's tile: 256 (C >= 256 layers) or 128 (the C = 128 k7 layers)
+__global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmBh,
+                                                                  const __grid_constant__ CUtensorMap tmR,
+                                                                  const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
   constexpr int BK = 64;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,15 +111,28 @@ __global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_c
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
   auto tempty_bar = [&](int i) { return bars + 8u * (2 * a.stages + 2 + i); };
   const uint32_t tmem_slot = bars + 8u * (2 * a.stages + 4);
+  // RES: group g's [CW / 64][128 rows][128 B] SWIZZLE_128B tile buffer (residual in, result out) at bars + 1024 + g (RBUF + 1024),
+  // then its bias copy; rfull[g] = residual landed (this CTA's own barrier), rempty[g] = the previous result has left the buffer
+  constexpr int NG = RES ? kCg2ResGroups : 1;      // epilogue groups
+  constexpr int CW = kCg2BN / NG;                  // columns per group
+  constexpr uint32_t RBUF = (uint32_t)BM * CW * 2u;
+  auto rfull_bar = [&](int g) { return bars + 384u + 8u * g; };
+  auto rempty_bar = [&](int g) { return bars + 416u + 8u * g; };
+  auto rbuf = [&](int g) { return bars + 1024u + (uint32_t)g * (RBUF + 1024u); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8 * NG); }
+    for (int g = 0; g < NG; ++g) { mbar_init(rfull_bar(g), 1); mbar_init(rempty_bar(g), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+    if (RES) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    }
   }
   if (warp == 1) {   // both CTAs of the pair allocate together (same warp id, same destination offset)
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * kCg2BN)) : "memory");
@@ -119,6 +168,8 @@ __global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_c
       for (int it = 0; it < my_units; ++it) {
         int b, m0, n0;
         unit_coords(it, b, m0, n0);
+        if (RES && a.res_tma > 1)   // this tile's residual -> L2 now, so that the load below (issued once the buffers are free) is short
+          for (int bx = 0; bx < kCg2BN / 64; ++bx) tma_prefetch_3d(&tmR, n0 + 64 * bx, m0, b);
         for (int q = 0; q < a.n_chunks; ++q) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (rank == 0) mbar_expect_tx(full_bar(s), 2u * STAGE);           // the leader's barrier counts both CTAs' bytes
@@ -126,6 +177,13 @@ __global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_c
           tma2_load_3d(sa, &tmA, full_bar(s), a.chunk_col[q], m0 + a.chunk_off[q], b);
           tma2_load_2d(sa + A_BYTES, &tmBh, full_bar(s), q * BK, n0 + (int)rank * (kCg2BN / 2));
           if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+        if (RES) {   // this CTA's residual tile, one column half per epilogue group, on the CTA's OWN barriers
+          for (int g = 0; g < NG; ++g) {
+            if (it > 0) mbar_wait(rempty_bar(g), (uint32_t)(it - 1) & 1u);
+            mbar_expect_tx(rfull_bar(g), RBUF);
+            for (int bx = 0; bx < CW / 64; ++bx) tma_load_3d(rbuf(g) + (uint32_t)bx * 16384u, &tmR, rfull_bar(g), n0 + g * CW + 64 * bx, m0, b);
+          }
         }
       }
     }
@@ -164,6 +222,78 @@ __global__ void __launch_bounds__(kCg2Threads, 1) conv_tc2_kernel(const __grid_c
     const uint32_t sbias = stg + (uint32_t)BM * RS;
     const uint32_t tempty0 = map_to_cta(tempty_bar(0), 0u), tempty1 = map_to_cta(tempty_bar(1), 0u);
     int bias_n0 = -1;
+    if constexpr (RES) {
+      const int grp = (warp - 2) >> 2;                     // column slice of this group
+      const int bar_id = 1 + grp;
+      const uint32_t buf = rbuf(grp), gbias = buf + RBUF;
+      const uint32_t rrow = buf + (uint32_t)row_in_tile * 128u;
+      const uint32_t rx = (uint32_t)(row_in_tile & 7);
+      for (int it = 0; it < my_units; ++it) {
+        const int acc = it & 1;
+        int b, m0, n0;
+        unit_coords(it, b, m0, n0);
+        const bool valid = m0 + row_in_tile < a.lout;
+        const int nc = n0 + grp * CW;
+        if (n0 != bias_n0) {
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          for (int i = et; i < CW; i += 128) {
+            const float bv = (nc + i < a.cout) ? __ldg(a.bias + nc + i) : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(gbias + 4u * i), "f"(bv) : "memory");
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          bias_n0 = n0;
+        }
+        mbar_wait(tfull_bar(acc), ((uint32_t)(it >> 1)) & 1u);
+        tc_fence_after();
+        mbar_wait(rfull_bar(grp), (uint32_t)it & 1u);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kCg2BN + grp * CW);
+        uint32_t vv[CW / 32][32];
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) tmem_ld32_nowait(taddr + 32u * h, vv[h]);
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) tmem_ld_wait32(vv[h]);
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) {
+          const int c0 = 32 * h;
+          uint32_t(&v)[32] = vv[h];
+          float bia[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bia[j]), "=f"(bia[j + 1]), "=f"(bia[j + 2]), "=f"(bia[j + 3])
+                         : "r"(gbias + 4u * (uint32_t)(c0 + j)));
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t col = (uint32_t)c0 + 8u * g;
+            const uint32_t addr = rrow + (col >> 6) * 16384u + ((((col & 63u) >> 3) ^ rx) << 4);
+            float2 y0 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(bia[8 * g + 0], bia[8 * g + 1]));
+            float2 y1 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(bia[8 * g + 2], bia[8 * g + 3]));
+            float2 y2 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bia[8 * g + 4], bia[8 * g + 5]));
+            float2 y3 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bia[8 * g + 6], bia[8 * g + 7]));
+            uint4 rres;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres.x), "=r"(rres.y), "=r"(rres.z), "=r"(rres.w) : "r"(addr));
+            y0 = __fadd2_rn(y0, unpack_bf16(rres.x));
+            y1 = __fadd2_rn(y1, unpack_bf16(rres.y));
+            y2 = __fadd2_rn(y2, unpack_bf16(rres.z));
+            y3 = __fadd2_rn(y3, unpack_bf16(rres.w));
+            uint4 o = make_uint4(pack_bf16(elu2(y0)), pack_bf16(elu2(y1)), pack_bf16(elu2(y2)), pack_bf16(elu2(y3)));
+            if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+        }
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is read by the TMA store (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? tempty1 : tempty0);   // 8 NG arrivals: NG groups x 4 warps x 2 CTAs
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // the group's half tile is complete in the buffer
+        if (et == 0) {
+          for (int bx = 0; bx < CW / 64; ++bx) tma_store_3d(&tmO, buf + (uint32_t)bx * 16384u, nc + 64 * bx, m0, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has read the buffer: the next residual may land
+          mbar_arrive(rempty_bar(grp));
+        }
+      }
+      if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's tile stores are complete
+    } else
     for (int it = 0; it < my_units; ++it) {
       const int acc = it & 1;
       int b, m0, n0;

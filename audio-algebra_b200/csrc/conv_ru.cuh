@@ -51,10 +51,22 @@ struct RuCfg {
   static constexpr int OFF_W7 = 2048;
   static constexpr int OFF_W1 = OFF_W7 + W7BYTES;
   static constexpr int OFF_X = OFF_W1 + W1BYTES;
-  static constexpr int NG = 2;                           // epilogue groups (4 warps each); C = 32 runs two CTAs per SM instead
+#ifndef AA_RU_NG32
+#define AA_RU_NG32 2
+#endif
+#ifndef AA_RU_NG64
+#define AA_RU_NG64 2
+#endif
+#ifndef AA_RU_NX32
+#define AA_RU_NX32 6
+#endif
+#ifndef AA_RU_NX64
+#define AA_RU_NX64 4
+#endif
+  static constexpr int NG = (C == 32) ? AA_RU_NG32 : (C == 64) ? AA_RU_NG64 : 2;   // epilogue groups (4 warps each) = tiles in flight per CTA; C = 32 also runs two CTAs per SM
   static constexpr int EPI0 = STREAM ? 3 : 2;            // first epilogue warp (warp 0: x producer, 1: MMA issuer, 2: weight producer if STREAM)
   static constexpr int THREADS = 32 * EPI0 + 128 * NG;
-  static constexpr int NX = (C == 32) ? 6 : (C == 64) ? 4 : 2;   // x tiles in flight (a stage is held until its tile's phase 2 has read the residual)
+  static constexpr int NX = (C == 32) ? AA_RU_NX32 : (C == 64) ? AA_RU_NX64 : 2;   // x tiles in flight (a stage is held until its tile's phase 2 has read the residual)
   // the 1x1 conv of tile i is issued after the k7 conv of tile i + LAG; LAG <= NX - 1, otherwise the x stage that tile
   // i + LAG needs would only be released by a phase 2 that waits for that very 1x1 conv
   static constexpr int LAG = (NG - 1 < NX - 1) ? NG - 1 : NX - 1;

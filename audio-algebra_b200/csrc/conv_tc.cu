@@ -817,6 +817,7 @@ struct TcState {
   int bn_1x1_wide = 0;
   int nepi_k7_128 = 0, nacc_min = 0;
   int cg2 = 1;                 // wide non-residual layers as cta_group::2 MMAs on CTA pairs (conv_cg2.cuh; AA_TC_CG2=0: one CTA per tile)
+  int cg2r = 1;                // ResidualUnit 1x1 layers at C >= 256 on CTA pairs (conv_tc2_kernel<256, true>; AA_TC_CG2R=0: one CTA per tile, 2: + L2 prefetch of the residual)
   int res_tma = 1;             // ResidualUnit 1x1 layers: residual / result tiles through TMA (AA_RES_TMA=0: per-thread loads, staged stores)
 };
 
@@ -865,8 +866,9 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
-  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
-  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+  AA_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_c32k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
   AA_CUDA(cudaFuncSetAttribute(conv_l0_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0Smem));
@@ -890,6 +892,7 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   if (getenv("AA_TC_NEPI128")) st->nepi_k7_128 = atoi(getenv("AA_TC_NEPI128"));
   if (getenv("AA_TC_NACC")) st->nacc_min = atoi(getenv("AA_TC_NACC"));
   if (getenv("AA_TC_CG2")) st->cg2 = atoi(getenv("AA_TC_CG2"));
+  if (getenv("AA_TC_CG2R")) st->cg2r = atoi(getenv("AA_TC_CG2R"));
   if (getenv("AA_DEBUG")) fprintf(stderr, "[aa] ru_fused CTAs/SM: C=32 -> %d, C=64 -> %d\n", st->ru_ctas_per_sm[0], st->ru_ctas_per_sm[1]);
   *out = st;
   return AA_OK;
@@ -1040,6 +1043,11 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     // (The C = 512 1x1 layers measured 113 us at bn = 128, 110 us at bn = 256 with res_tma, 147 us at bn = 256 without: unchanged
     //  unless the dev knob AA_1X1_BN256=1 is set.)
     if (n_chunks_total == 8 && !last && ly.cout >= 256 && (ly.role != ROLE_RES_SECOND || st->bn_1x1_wide)) bn = 256;
+    // ResidualUnit 1x1 layers at C >= 512: 256-wide tiles on CTA pairs (conv_tc2_kernel<256, true>); measured at B = 64: C = 512
+    // 110 -> 94 us (403 MB of activations = 61 us at the HBM roofline), C = 256 78 -> 79 us (kept on conv_tc_kernel unless AA_TC_CG2R=3)
+    const bool pair_res = st->cg2 && st->cg2r && ly.role == ROLE_RES_SECOND && !last && p.bk == 64 && p.n_taps == 1 && ly.cout % 256 == 0 &&
+                          (ly.cout >= 512 || st->cg2r >= 3) && ly.elu && rows_padded(lout) >= 2 * BM && aa::num_sms() >= 2;
+    if (pair_res) bn = 256;
     {
       cuuint64_t dims[2] = {(cuuint64_t)p.k_total, (cuuint64_t)ly.cout};
       cuuint64_t strides[1] = {(cuuint64_t)p.k_total * 2};
@@ -1078,6 +1086,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     // (measured per layer at B = 64: C = 128 95 -> 67 us, C = 256 98 -> 79 us; C = 512 -- 8 K chunks, bound by re-streaming the
     //  weights from L2 for every tile -- 110 -> 120 us: those layers keep the per-thread path unless AA_RES_TMA=2)
     a.res_tma = (a.res != nullptr && !last && bn % 64 == 0 && (st->res_tma > 1 || (st->res_tma == 1 && n_chunks_total <= 4))) ? 1 : 0;
+    if (pair_res) a.res_tma = st->cg2r;   // the pair kernel always takes the TMA route (2: with the L2 prefetch)
     const int staging = a.res_tma ? 512 + a.n_epi * (BM * bn * 2 + 1024) : a.n_epi * ((last ? 0 : BM * (bn * 2 + 16)) + bn * 4);
     a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging) / stage_bytes));
     const int smem = a.stages * stage_bytes + 1024 + 512 + staging;
@@ -1094,13 +1103,13 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(result) failed for layer %zu: %d", i, (int)r);
     }
-    AA_REQUIRE(smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);
+    AA_REQUIRE(pair_res || smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);
     const int grid = (int)std::min<long long>(a.tiles, aa::num_sms());
     const int threads = 64 + 128 * a.n_epi;
     AA_REQUIRE(last || ly.elu, "bf16 layers without ELU are not supported on the tensor-core path (layer %zu)", i);
     const bool res = a.res != nullptr;
     // (bn = 128 pairs -- AA_TC_CG2=2 -- measured SLOWER: C = 128 k7 120 -> 133 us, 64 -> 128 down-conv 102 -> 110 us; off)
-    if (st->cg2 && !res && !last && p.bk == 64 && (bn == 256 || (bn == 128 && st->cg2 > 1)) && ly.cout % bn == 0 && a.m_tiles >= 2 && aa::num_sms() >= 2) {
+    if (pair_res || (st->cg2 && !res && !last && p.bk == 64 && (bn == 256 || (bn == 128 && st->cg2 > 1)) && ly.cout % bn == 0 && a.m_tiles >= 2 && aa::num_sms() >= 2)) {
       const int kCg2BN = bn;
       // wide non-residual layer: CTA pairs, M = 256 cta_group::2 MMAs, each CTA loads half of the weight box (conv_cg2.cuh)
       CUtensorMap tmBh;
@@ -1112,18 +1121,20 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B half) failed for layer %zu: %d", i, (int)r);
       const int stage2 = BM * 64 * 2 + (kCg2BN / 2) * 64 * 2;
-      const int fixed = 1024 + 512 + BM * (kCg2BN * 2 + 16) + kCg2BN * 4 + 256;
+      const int fixed = pair_res ? 1024 + 1024 + kCg2ResGroups * (BM * (kCg2BN / kCg2ResGroups) * 2 + 1024) : 1024 + 512 + BM * (kCg2BN * 2 + 16) + kCg2BN * 4 + 256;
       a.stages = std::max(2, std::min(8, (st->max_smem - fixed) / stage2));
       const int smem2 = a.stages * stage2 + fixed;
       const long long units = batch * ((a.m_tiles + 1) / 2) * a.n_tiles_n;
       const int grid2 = (int)std::min<long long>(2 * units, (long long)(aa::num_sms() & ~1));
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3((unsigned)kCg2Threads); cfg.dynamicSmemBytes = (size_t)smem2; cfg.stream = stream;
+      cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3((unsigned)(pair_res ? kCg2ResThreads : kCg2Threads)); cfg.dynamicSmemBytes = (size_t)smem2; cfg.stream = stream;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      cudaError_t le = bn == 256 ? cudaLaunchKernelEx(&cfg, conv_tc2_kernel<256>, tmA, tmBh, a) : cudaLaunchKernelEx(&cfg, conv_tc2_kernel<128>, tmA, tmBh, a);
+      cudaError_t le = pair_res   ? cudaLaunchKernelEx(&cfg, conv_tc2_kernel<256, true>, tmA, tmBh, tmR, tmO, a)
+                       : bn == 256 ? cudaLaunchKernelEx(&cfg, conv_tc2_kernel<256, false>, tmA, tmBh, tmR, tmO, a)
+                                   : cudaLaunchKernelEx(&cfg, conv_tc2_kernel<128, false>, tmA, tmBh, tmR, tmO, a);
       AA_REQUIRE(le == cudaSuccess, "conv_tc2_kernel launch failed for layer %zu: %s", i, cudaGetErrorString(le));
       AA_LAUNCH_CHECK();
       if (ly.role == ROLE_RES_SECOND) res_buf = -1;
