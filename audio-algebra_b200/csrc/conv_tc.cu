@@ -49,6 +49,9 @@ struct TcArgs {
   long long out_row_stride;         // rows per batch element in `out` / `res`
   int elu, tanh_out;
   int res_tma;                      // RES layers with bn % 64 == 0: residual tile in / result tile out through TMA (see the epilogue)
+  // halo mode (stride-1 k-tap layers, non-RES): ONE [halo_rows x 64 channels] activation box per channel chunk serves all taps
+  // (tap j = the same box with the descriptor start advanced by j * dil rows), only the weight boxes stream per (chunk, tap)
+  int halo_rows, halo_cc, halo_taps, halo_dil, halo_row0, a_stages;   // rows of the box, channel chunks, taps, dilation, row offset of tap 0, A slots
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -163,8 +166,11 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
   constexpr uint32_t A_BYTES = BM * BK * 2;
   const uint32_t B_BYTES = (uint32_t)a.bn * BK * 2;
-  const uint32_t STAGE = A_BYTES + ((B_BYTES + 1023u) & ~1023u);
-  const uint32_t bars = base + (uint32_t)a.stages * STAGE;              // full[S], empty[S], tfull[8], tempty[8], tmem ptr
+  const bool halo = !RES && a.halo_rows > 0;
+  const uint32_t HALO_SLOT = halo ? (((uint32_t)a.halo_rows * (uint32_t)(BK * 2) + 1023u) & ~1023u) : 0u;   // A slots come first
+  const uint32_t STAGE = (halo ? 0u : A_BYTES) + ((B_BYTES + 1023u) & ~1023u);
+  const uint32_t ring = base + (uint32_t)a.a_stages * HALO_SLOT;       // operand ring (halo mode: weight boxes only)
+  const uint32_t bars = ring + (uint32_t)a.stages * STAGE;              // full[S], empty[S], tfull[8], tempty[8], tmem ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
@@ -184,6 +190,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int i = 0; i < a.n_acc; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
     for (int g = 0; g < kMaxEpi; ++g) { mbar_init(rfull_bar(g), 1); mbar_init(rempty_bar(g), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bars + 448u + 8u * i, 1); mbar_init(bars + 480u + 8u * i, 1); }   // afull[4], aempty[4] (halo mode)
+    if (halo) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");   // tmR = the halo box map in this mode
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -210,18 +218,40 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues: see elect_one) =====================
     {
       const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
-      int s = 0;
-      uint32_t ph = 0;
+      const uint32_t uring = __shfl_sync(0xffffffffu, ring, 0);
+      int s = 0, has = 0;
+      uint32_t ph = 0, hph = 0;
       int it = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int b = (int)(t / tiles_per_b);
         const int r = (int)(t % tiles_per_b);
         const int nt = r % a.n_tiles_n, mt = r / a.n_tiles_n;
         const int m0 = mt * BM, n0 = nt * a.bn;
+        if (halo) {
+          for (int cc = 0; cc < a.halo_cc; ++cc) {
+            const uint32_t af = ubars + 448u + 8u * has;
+            mbar_wait(ubars + 480u + 8u * has, hph ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(af, (uint32_t)a.halo_rows * (uint32_t)(BK * 2));
+              tma_load_3d(ubase + (uint32_t)has * HALO_SLOT, &tmR, af, cc * BK, m0 + a.halo_row0, b);
+            }
+            if (++has == a.a_stages) { has = 0; hph ^= 1u; }
+            for (int j = 0; j < a.halo_taps; ++j) {
+              const uint32_t fb = ubars + 8u * s;
+              mbar_wait(ubars + 8u * (a.stages + s), ph ^ 1u);
+              if (elect_one()) {
+                mbar_expect_tx(fb, B_BYTES);
+                tma_load_2d(uring + (uint32_t)s * STAGE, &tmB, fb, (j * a.halo_cc + cc) * BK, n0);
+              }
+              if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+          }
+          continue;
+        }
         for (int q = 0; q < a.n_chunks; ++q) {
           const uint32_t fb = ubars + 8u * s;
           mbar_wait(ubars + 8u * (a.stages + s), ph ^ 1u);
-          const uint32_t sa = ubase + (uint32_t)s * STAGE;
+          const uint32_t sa = uring + (uint32_t)s * STAGE;
           if (elect_one()) {
             mbar_expect_tx(fb, A_BYTES + B_BYTES);
             tma_load_3d(sa, &tmA, fb, a.chunk_col[q], m0 + a.chunk_off[q], b);
@@ -248,20 +278,43 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
     {
       const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
       const uint32_t utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t uring = __shfl_sync(0xffffffffu, ring, 0);
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, has = 0;
+      uint32_t ph = 0, hph = 0;
       int it = 0;
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int acc = it % a.n_acc;
         mbar_wait(ubars + 8u * (2 * a.stages + kMaxAcc + acc), (((uint32_t)(it / a.n_acc)) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = utmem + (uint32_t)(acc * a.bn);
+        if (halo) {
+          for (int cc = 0; cc < a.halo_cc; ++cc) {
+            mbar_wait(ubars + 448u + 8u * has, hph);
+            const uint32_t xa = ubase + (uint32_t)has * HALO_SLOT;
+            for (int j = 0; j < a.halo_taps; ++j) {
+              mbar_wait(ubars + 8u * s, ph);
+              tc_fence_after();
+              // tap j = the halo box seen from row j * dil on (SWIZZLE_128B is a function of the shared-memory address, so a
+              // descriptor may start at any 128-byte row of a TMA-written tile: profiles/ubench/sw128_rowshift_ubench)
+              const uint64_t da = make_desc<BK>(xa + (uint32_t)(j * a.halo_dil) * (uint32_t)(BK * 2)), db = make_desc<BK>(uring + (uint32_t)s * STAGE);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                if (elect_one()) umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (cc | j | k) != 0 ? 1u : 0u);
+              if (elect_one()) umma_commit(ubars + 8u * (a.stages + s));   // frees the weight stage
+              if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+            if (elect_one()) umma_commit(ubars + 480u + 8u * has);         // frees the halo slot when all its taps have been read
+            if (++has == a.a_stages) { has = 0; hph ^= 1u; }
+          }
+          if (elect_one()) umma_commit(ubars + 8u * (2 * a.stages + acc));
+          continue;
+        }
         for (int q = 0; q < a.n_chunks; ++q) {
           mbar_wait(ubars + 8u * s, ph);
           tc_fence_after();
-          const uint32_t sa = ubase + (uint32_t)s * STAGE;
+          const uint32_t sa = uring + (uint32_t)s * STAGE;
           const uint64_t da = make_desc<BK>(sa), db = make_desc<BK>(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)   // 16 bf16 = 32 bytes along K inside the swizzle atom
@@ -817,6 +870,7 @@ struct TcState {
   int bn_1x1_wide = 0;
   int nepi_k7_128 = 0, nacc_min = 0;
   int cg2 = 1;                 // wide non-residual layers as cta_group::2 MMAs on CTA pairs (conv_cg2.cuh; AA_TC_CG2=0: one CTA per tile)
+  int halo = 1, halo_slots = 2;   // conv_tc_kernel halo mode (AA_TC_HALO=0: one activation box per tap; AA_TC_HALO_SLOTS: halo boxes in flight)
   int cg2r = 1;                // ResidualUnit 1x1 layers at C >= 256 on CTA pairs (conv_tc2_kernel<256, true>; AA_TC_CG2R=0: one CTA per tile, 2: + L2 prefetch of the residual)
   int res_tma = 1;             // ResidualUnit 1x1 layers: residual / result tiles through TMA (AA_RES_TMA=0: per-thread loads, staged stores)
 };
@@ -893,6 +947,8 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   if (getenv("AA_TC_NACC")) st->nacc_min = atoi(getenv("AA_TC_NACC"));
   if (getenv("AA_TC_CG2")) st->cg2 = atoi(getenv("AA_TC_CG2"));
   if (getenv("AA_TC_CG2R")) st->cg2r = atoi(getenv("AA_TC_CG2R"));
+  if (getenv("AA_TC_HALO")) st->halo = atoi(getenv("AA_TC_HALO"));
+  if (getenv("AA_TC_HALO_SLOTS")) st->halo_slots = std::max(1, std::min(4, atoi(getenv("AA_TC_HALO_SLOTS"))));
   if (getenv("AA_DEBUG")) fprintf(stderr, "[aa] ru_fused CTAs/SM: C=32 -> %d, C=64 -> %d\n", st->ru_ctas_per_sm[0], st->ru_ctas_per_sm[1]);
   *out = st;
   return AA_OK;
@@ -1089,8 +1145,27 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     if (pair_res) a.res_tma = st->cg2r;   // the pair kernel always takes the TMA route (2: with the L2 prefetch)
     const int staging = a.res_tma ? 512 + a.n_epi * (BM * bn * 2 + 1024) : a.n_epi * ((last ? 0 : BM * (bn * 2 + 16)) + bn * 4);
     a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging) / stage_bytes));
-    const int smem = a.stages * stage_bytes + 1024 + 512 + staging;
-    CUtensorMap tmR = tmA, tmO = tmA;   // placeholders unless res_tma
+    int smem = a.stages * stage_bytes + 1024 + 512 + staging;
+    const bool pair_plain = st->cg2 && a.res == nullptr && !last && p.bk == 64 && (bn == 256 || (bn == 128 && st->cg2 > 1)) && ly.cout % bn == 0 &&
+                            a.m_tiles >= 2 && aa::num_sms() >= 2;
+    // halo mode (conv_tc_kernel, the k7 layers that stay on one CTA per tile, i.e. C = 128): one activation box per channel chunk for all taps
+    CUtensorMap tmH = tmA;
+    if (st->halo && !pair_res && !pair_plain && a.res == nullptr && !last && ly.stride == 1 && p.n_taps >= 3 && p.bk == 64 && ly.cin % 64 == 0 &&
+        BM + (p.n_taps - 1) * ly.dil <= 256) {
+      a.halo_rows = BM + (p.n_taps - 1) * ly.dil; a.halo_cc = ly.cin / 64; a.halo_taps = p.n_taps; a.halo_dil = ly.dil; a.halo_row0 = p.tap_off[0];
+      const int slot = (a.halo_rows * 128 + 1023) & ~1023, bstage = (bn * 128 + 1023) & ~1023;
+      a.a_stages = st->halo_slots;
+      a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging - a.a_stages * slot) / bstage));
+      smem = a.a_stages * slot + a.stages * bstage + 1024 + 512 + staging;
+      cuuint64_t dims[3] = {(cuuint64_t)p.view_c, (cuuint64_t)view_rows, (cuuint64_t)batch};
+      cuuint64_t strides[2] = {(cuuint64_t)p.view_c * 2, (cuuint64_t)in_rows_alloc * ly.cin * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)a.halo_rows, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&tmH, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, buf[cur], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo box) failed for layer %zu: %d", i, (int)r);
+    }
+    CUtensorMap tmR = tmH, tmO = tmA;   // placeholders unless res_tma (tmR = the halo box map in halo mode)
     if (a.res_tma) {
       cuuint64_t dims[3] = {(cuuint64_t)ly.cout, (cuuint64_t)rows_padded(lout), (cuuint64_t)batch};
       cuuint64_t strides[2] = {(cuuint64_t)ly.cout * 2, (cuuint64_t)rows_padded(lout) * ly.cout * 2};
@@ -1109,7 +1184,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     AA_REQUIRE(last || ly.elu, "bf16 layers without ELU are not supported on the tensor-core path (layer %zu)", i);
     const bool res = a.res != nullptr;
     // (bn = 128 pairs -- AA_TC_CG2=2 -- measured SLOWER: C = 128 k7 120 -> 133 us, 64 -> 128 down-conv 102 -> 110 us; off)
-    if (pair_res || (st->cg2 && !res && !last && p.bk == 64 && (bn == 256 || (bn == 128 && st->cg2 > 1)) && ly.cout % bn == 0 && a.m_tiles >= 2 && aa::num_sms() >= 2)) {
+    if (pair_res || pair_plain) {
       const int kCg2BN = bn;
       // wide non-residual layer: CTA pairs, M = 256 cta_group::2 MMAs, each CTA loads half of the weight box (conv_cg2.cuh)
       CUtensorMap tmBh;

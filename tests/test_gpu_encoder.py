@@ -521,6 +521,7 @@ def test_cta_pair_layers_are_bit_identical_to_the_single_cta_kernel(setup):
 
     def make(cg2):
         os.environ["AA_TC_CG2"] = "1" if cg2 else "0"
+        os.environ["AA_TC_HALO"] = "0"   # the halo mode of conv_tc_kernel accumulates chunk-major, not tap-major: other rounding
         try:
             w = aab.DVAEWrapper(debug=False, compute_dtype="bf16")
             w.model.load_oracle_weights(enc_o)
@@ -528,6 +529,7 @@ def test_cta_pair_layers_are_bit_identical_to_the_single_cta_kernel(setup):
             w.encode(torch.zeros(1, 2, 1024, device="cuda"))   # the handle reads the switch at its first bf16 forward
         finally:
             os.environ.pop("AA_TC_CG2", None)
+            os.environ.pop("AA_TC_HALO", None)
         return w
 
     pair, single = make(True), make(False)
@@ -535,3 +537,51 @@ def test_cta_pair_layers_are_bit_identical_to_the_single_cta_kernel(setup):
         x = _x(shape, seed).cuda()
         a, b = pair.encode(x), single.encode(x)
         assert torch.equal(a, b), (shape, float((a - b).abs().max()))
+
+
+def test_halo_box_layers_match_the_per_tap_boxes(setup):
+    """conv_tc_kernel's halo mode (ONE [128 + 6 d rows x 64 channels] activation box per channel chunk, the seven taps as row-shifted
+    descriptor views of it; used by the k7 layers that stay on one CTA per tile -- C = 128 by default, every wide k7 layer with
+    AA_TC_CG2=0) against the per-tap boxes (AA_TC_HALO=0).  (1) Operands for which nothing rounds (one unit weight per output
+    channel, small integer inputs, zero biases): bit-identical through the whole 37-layer encoder, dilations 1 / 3 / 9, ragged
+    lengths, many tile seams.  (2) Oracle weights: the two accumulation orders agree to bf16 rounding."""
+    import os
+    aab, O, enc_o, dv = setup
+
+    def make(halo, cg2, exact):
+        os.environ["AA_TC_HALO"] = "1" if halo else "0"
+        os.environ["AA_TC_CG2"] = "1" if cg2 else "0"
+        try:
+            w = aab.DVAEWrapper(debug=False, compute_dtype="bf16")
+            if exact:
+                with torch.no_grad():
+                    for enc in (w.model.encoder, w.model.encoder_ema):
+                        for li, conv in enumerate(enc.flat_convs()):
+                            cout, cin, k = conv.weight.shape
+                            wt = torch.zeros(cout, cin, k)
+                            o = torch.arange(cout)
+                            wt[o, (o * 5 + li) % cin, (o + li) % k] = 0.125 if conv.stride[0] > 1 else 1.0
+                            conv.weight.copy_(wt)
+                            conv.bias.zero_()
+            else:
+                w.model.load_oracle_weights(enc_o)
+            w = w.cuda()
+            w.encode(torch.zeros(1, 2, 1024, device="cuda"))   # the handle reads the switches at its first bf16 forward
+        finally:
+            os.environ.pop("AA_TC_HALO", None)
+            os.environ.pop("AA_TC_CG2", None)
+        return w
+
+    for cg2 in (True, False):
+        on, off = make(True, cg2, True), make(False, cg2, True)
+        for shape, seed in [((2, 2, 131072), 51), ((3, 2, 128 * 256 * 3 + 1300), 52), ((1, 2, 70000), 53)]:
+            g = torch.Generator().manual_seed(seed)
+            x = torch.randint(0, 4, shape, generator=g).float().cuda()
+            a, b = on.encode(x), off.encode(x)
+            assert torch.equal(a, b), (cg2, shape, float((a - b).abs().max()))
+            assert a.abs().max() > 0
+        on, off = make(True, cg2, False), make(False, cg2, False)
+        for shape, seed in [((4, 2, 131072), 61), ((2, 2, 50000), 62)]:
+            x = _x(shape, seed).cuda()
+            a, b = on.encode(x), off.encode(x)
+            assert rel_l2(a.cpu(), b.cpu()) < 5e-3, (cg2, shape, rel_l2(a.cpu(), b.cpu()))
