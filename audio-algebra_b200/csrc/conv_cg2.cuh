@@ -104,8 +104,16 @@ __global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc
   constexpr int BK = 64;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t A_BYTES = BM * BK * 2, BH_BYTES = (kCg2BN / 2) * BK * 2, STAGE = A_BYTES + BH_BYTES;
-  const uint32_t bars = base + (uint32_t)a.stages * STAGE;   // full[S], empty[S], tfull[2], tempty[2], tmem slot
+  constexpr uint32_t A_BYTES = BM * BK * 2, BH_BYTES = (kCg2BN / 2) * BK * 2;
+  // halo mode (non-RES k-tap layers, as in conv_tc_kernel): one [halo_rows x 64] activation box per channel chunk in its own ring
+  // (afull / aempty at bars + 448 / 480), the operand ring then carries the weight halves only
+  const bool halo = !RES && a.halo_rows > 0;
+  const uint32_t HALO_BYTES = (uint32_t)a.halo_rows * (uint32_t)(BK * 2), HALO_SLOT = halo ? ((HALO_BYTES + 1023u) & ~1023u) : 0u;
+  const uint32_t STAGE = halo ? BH_BYTES : A_BYTES + BH_BYTES;
+  const uint32_t ring = base + (uint32_t)a.a_stages * HALO_SLOT;
+  const uint32_t bars = ring + (uint32_t)a.stages * STAGE;   // full[S], empty[S], tfull[2], tempty[2], tmem slot
+  auto afull_bar = [&](int i) { return bars + 448u + 8u * i; };
+  auto aempty_bar = [&](int i) { return bars + 480u + 8u * i; };
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
@@ -126,6 +134,8 @@ __global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8 * NG); }
     for (int g = 0; g < NG; ++g) { mbar_init(rfull_bar(g), 1); mbar_init(rempty_bar(g), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(afull_bar(i), 1); mbar_init(aempty_bar(i), 1); }
+    if (halo) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");   // tmR = the halo box map in this mode
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
@@ -163,17 +173,32 @@ __global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, has = 0;
+      uint32_t ph = 0, hph = 0;
       for (int it = 0; it < my_units; ++it) {
         int b, m0, n0;
         unit_coords(it, b, m0, n0);
+        if (halo) {
+          for (int cc = 0; cc < a.halo_cc; ++cc) {
+            mbar_wait(aempty_bar(has), hph ^ 1u);
+            if (rank == 0) mbar_expect_tx(afull_bar(has), 2u * HALO_BYTES);
+            tma2_load_3d(base + (uint32_t)has * HALO_SLOT, &tmR, afull_bar(has), cc * BK, m0 + a.halo_row0, b);
+            if (++has == a.a_stages) { has = 0; hph ^= 1u; }
+            for (int j = 0; j < a.halo_taps; ++j) {
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              if (rank == 0) mbar_expect_tx(full_bar(s), 2u * BH_BYTES);
+              tma2_load_2d(ring + (uint32_t)s * STAGE, &tmBh, full_bar(s), (j * a.halo_cc + cc) * BK, n0 + (int)rank * (kCg2BN / 2));
+              if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+          }
+          continue;
+        }
         if (RES && a.res_tma > 1)   // this tile's residual -> L2 now, so that the load below (issued once the buffers are free) is short
           for (int bx = 0; bx < kCg2BN / 64; ++bx) tma_prefetch_3d(&tmR, n0 + 64 * bx, m0, b);
         for (int q = 0; q < a.n_chunks; ++q) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (rank == 0) mbar_expect_tx(full_bar(s), 2u * STAGE);           // the leader's barrier counts both CTAs' bytes
-          const uint32_t sa = base + (uint32_t)s * STAGE;
+          const uint32_t sa = ring + (uint32_t)s * STAGE;
           tma2_load_3d(sa, &tmA, full_bar(s), a.chunk_col[q], m0 + a.chunk_off[q], b);
           tma2_load_2d(sa + A_BYTES, &tmBh, full_bar(s), q * BK, n0 + (int)rank * (kCg2BN / 2));
           if (++s == a.stages) { s = 0; ph ^= 1u; }
@@ -192,17 +217,36 @@ __global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc
     if (rank == 0 && lane == 0) {
       // D = F32, A = B = BF16, K-major, N = 256, M = 256 (cta_group::2)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCg2BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, has = 0;
+      uint32_t ph = 0, hph = 0;
       for (int it = 0; it < my_units; ++it) {
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), (((uint32_t)(it >> 1)) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kCg2BN);
+        if (halo) {
+          for (int cc = 0; cc < a.halo_cc; ++cc) {
+            mbar_wait(afull_bar(has), hph);
+            const uint32_t xa = base + (uint32_t)has * HALO_SLOT;
+            for (int j = 0; j < a.halo_taps; ++j) {
+              mbar_wait(full_bar(s), ph);
+              tc_fence_after();
+              const uint64_t da = make_desc<BK>(xa + (uint32_t)(j * a.halo_dil) * (uint32_t)(BK * 2)), db = make_desc<BK>(ring + (uint32_t)s * STAGE);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (cc | j | k) != 0 ? 1u : 0u);
+              umma2_commit_mc(empty_bar(s), (uint16_t)3);
+              if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+            umma2_commit_mc(aempty_bar(has), (uint16_t)3);   // the halo slots of both CTAs are free once all taps have read them
+            if (++has == a.a_stages) { has = 0; hph ^= 1u; }
+          }
+          umma2_commit_mc(tfull_bar(acc), (uint16_t)3);
+          continue;
+        }
         for (int q = 0; q < a.n_chunks; ++q) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = base + (uint32_t)s * STAGE;
+          const uint32_t sa = ring + (uint32_t)s * STAGE;
           const uint64_t da = make_desc<BK>(sa), db = make_desc<BK>(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (q | k) != 0 ? 1u : 0u);

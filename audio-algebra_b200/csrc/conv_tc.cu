@@ -870,7 +870,7 @@ struct TcState {
   int bn_1x1_wide = 0;
   int nepi_k7_128 = 0, nacc_min = 0;
   int cg2 = 1;                 // wide non-residual layers as cta_group::2 MMAs on CTA pairs (conv_cg2.cuh; AA_TC_CG2=0: one CTA per tile)
-  int halo = 1, halo_slots = 2;   // conv_tc_kernel halo mode (AA_TC_HALO=0: one activation box per tap; AA_TC_HALO_SLOTS: halo boxes in flight)
+  int halo = 1, halo_slots = 2;   // halo mode of the k-tap layers (AA_TC_HALO=0: one activation box per tap, 2: single-CTA kernel only, 3: also N = 128 pairs -- measured slower; AA_TC_HALO_SLOTS: halo boxes in flight)
   int cg2r = 1;                // ResidualUnit 1x1 layers at C >= 256 on CTA pairs (conv_tc2_kernel<256, true>; AA_TC_CG2R=0: one CTA per tile, 2: + L2 prefetch of the residual)
   int res_tma = 1;             // ResidualUnit 1x1 layers: residual / result tiles through TMA (AA_RES_TMA=0: per-thread loads, staged stores)
 };
@@ -1146,12 +1146,14 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     const int staging = a.res_tma ? 512 + a.n_epi * (BM * bn * 2 + 1024) : a.n_epi * ((last ? 0 : BM * (bn * 2 + 16)) + bn * 4);
     a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging) / stage_bytes));
     int smem = a.stages * stage_bytes + 1024 + 512 + staging;
-    const bool pair_plain = st->cg2 && a.res == nullptr && !last && p.bk == 64 && (bn == 256 || (bn == 128 && st->cg2 > 1)) && ly.cout % bn == 0 &&
+    const bool halo_shape = a.res == nullptr && !last && ly.stride == 1 && p.n_taps >= 3 && p.bk == 64 && ly.cin % 64 == 0 &&
+                            BM + (p.n_taps - 1) * ly.dil <= 256;
+    const bool pair_plain = st->cg2 && a.res == nullptr && !last && p.bk == 64 &&
+                            (bn == 256 || (bn == 128 && (st->cg2 > 1 || (st->halo >= 3 && halo_shape)))) && ly.cout % bn == 0 &&
                             a.m_tiles >= 2 && aa::num_sms() >= 2;
     // halo mode (conv_tc_kernel, the k7 layers that stay on one CTA per tile, i.e. C = 128): one activation box per channel chunk for all taps
     CUtensorMap tmH = tmA;
-    if (st->halo && !pair_res && !pair_plain && a.res == nullptr && !last && ly.stride == 1 && p.n_taps >= 3 && p.bk == 64 && ly.cin % 64 == 0 &&
-        BM + (p.n_taps - 1) * ly.dil <= 256) {
+    if (halo_shape && !pair_res && (pair_plain ? st->halo != 2 && st->halo >= 1 : st->halo >= 1)) {
       a.halo_rows = BM + (p.n_taps - 1) * ly.dil; a.halo_cc = ly.cin / 64; a.halo_taps = p.n_taps; a.halo_dil = ly.dil; a.halo_row0 = p.tap_off[0];
       const int slot = (a.halo_rows * 128 + 1023) & ~1023, bstage = (bn * 128 + 1023) & ~1023;
       a.a_stages = st->halo_slots;
@@ -1178,7 +1180,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(result) failed for layer %zu: %d", i, (int)r);
     }
-    AA_REQUIRE(pair_res || smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);
+    AA_REQUIRE(pair_res || pair_plain || smem <= st->max_smem, "layer %zu does not fit in shared memory (%d bytes)", i, smem);
     const int grid = (int)std::min<long long>(a.tiles, aa::num_sms());
     const int threads = 64 + 128 * a.n_epi;
     AA_REQUIRE(last || ly.elu, "bf16 layers without ELU are not supported on the tensor-core path (layer %zu)", i);
@@ -1198,7 +1200,13 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
       const int stage2 = BM * 64 * 2 + (kCg2BN / 2) * 64 * 2;
       const int fixed = pair_res ? 1024 + 1024 + kCg2ResGroups * (BM * (kCg2BN / kCg2ResGroups) * 2 + 1024) : 1024 + 512 + BM * (kCg2BN * 2 + 16) + kCg2BN * 4 + 256;
       a.stages = std::max(2, std::min(8, (st->max_smem - fixed) / stage2));
-      const int smem2 = a.stages * stage2 + fixed;
+      int smem2 = a.stages * stage2 + fixed;
+      if (a.halo_rows > 0) {   // halo mode: A slots + a ring of weight halves
+        const int slot = (a.halo_rows * 128 + 1023) & ~1023, bh = (kCg2BN / 2) * 64 * 2;
+        a.stages = std::max(2, std::min(8, (st->max_smem - fixed - a.a_stages * slot) / bh));
+        smem2 = a.a_stages * slot + a.stages * bh + fixed;
+      }
+      AA_REQUIRE(smem2 <= st->max_smem, "pair layer %zu does not fit in shared memory (%d bytes)", i, smem2);
       const long long units = batch * ((a.m_tiles + 1) / 2) * a.n_tiles_n;
       const int grid2 = (int)std::min<long long>(2 * units, (long long)(aa::num_sms() & ~1));
       cudaLaunchConfig_t cfg = {};

@@ -572,7 +572,7 @@ def test_halo_box_layers_match_the_per_tap_boxes(setup):
             os.environ.pop("AA_TC_CG2", None)
         return w
 
-    for cg2 in (True, False):
+    for cg2 in (True, False):   # with the pair kernel (its own halo ring, both CTAs' boxes on the leader's barrier) and without
         on, off = make(True, cg2, True), make(False, cg2, True)
         for shape, seed in [((2, 2, 131072), 51), ((3, 2, 128 * 256 * 3 + 1300), 52), ((1, 2, 70000), 53)]:
             g = torch.Generator().manual_seed(seed)
