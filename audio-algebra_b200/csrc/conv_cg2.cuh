@@ -171,8 +171,12 @@ __global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc
   };
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; whole warp runs the loop, one elected lane issues: see elect_one) =====================
+    {
+      const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
+      const uint32_t uring = __shfl_sync(0xffffffffu, ring, 0), urank = __shfl_sync(0xffffffffu, rank, 0);
+      auto ufull = [&](int s) { return ubars + 8u * s; };
+      auto uempty = [&](int s) { return ubars + 8u * (a.stages + s); };
       int s = 0, has = 0;
       uint32_t ph = 0, hph = 0;
       for (int it = 0; it < my_units; ++it) {
@@ -180,80 +184,99 @@ __global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc
         unit_coords(it, b, m0, n0);
         if (halo) {
           for (int cc = 0; cc < a.halo_cc; ++cc) {
-            mbar_wait(aempty_bar(has), hph ^ 1u);
-            if (rank == 0) mbar_expect_tx(afull_bar(has), 2u * HALO_BYTES);
-            tma2_load_3d(base + (uint32_t)has * HALO_SLOT, &tmR, afull_bar(has), cc * BK, m0 + a.halo_row0, b);
+            mbar_wait(ubars + 480u + 8u * has, hph ^ 1u);
+            if (elect_one()) {
+              if (urank == 0) mbar_expect_tx(ubars + 448u + 8u * has, 2u * HALO_BYTES);
+              tma2_load_3d(ubase + (uint32_t)has * HALO_SLOT, &tmR, ubars + 448u + 8u * has, cc * BK, m0 + a.halo_row0, b);
+            }
             if (++has == a.a_stages) { has = 0; hph ^= 1u; }
             for (int j = 0; j < a.halo_taps; ++j) {
-              mbar_wait(empty_bar(s), ph ^ 1u);
-              if (rank == 0) mbar_expect_tx(full_bar(s), 2u * BH_BYTES);
-              tma2_load_2d(ring + (uint32_t)s * STAGE, &tmBh, full_bar(s), (j * a.halo_cc + cc) * BK, n0 + (int)rank * (kCg2BN / 2));
+              mbar_wait(uempty(s), ph ^ 1u);
+              if (elect_one()) {
+                if (urank == 0) mbar_expect_tx(ufull(s), 2u * BH_BYTES);
+                tma2_load_2d(uring + (uint32_t)s * STAGE, &tmBh, ufull(s), (j * a.halo_cc + cc) * BK, n0 + (int)urank * (kCg2BN / 2));
+              }
               if (++s == a.stages) { s = 0; ph ^= 1u; }
             }
           }
           continue;
         }
-        if (RES && a.res_tma > 1)   // this tile's residual -> L2 now, so that the load below (issued once the buffers are free) is short
+        if (RES && a.res_tma > 1 && elect_one())   // this tile's residual -> L2 now, so that the load below (issued once the buffers are free) is short
           for (int bx = 0; bx < kCg2BN / 64; ++bx) tma_prefetch_3d(&tmR, n0 + 64 * bx, m0, b);
         for (int q = 0; q < a.n_chunks; ++q) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          if (rank == 0) mbar_expect_tx(full_bar(s), 2u * STAGE);           // the leader's barrier counts both CTAs' bytes
-          const uint32_t sa = ring + (uint32_t)s * STAGE;
-          tma2_load_3d(sa, &tmA, full_bar(s), a.chunk_col[q], m0 + a.chunk_off[q], b);
-          tma2_load_2d(sa + A_BYTES, &tmBh, full_bar(s), q * BK, n0 + (int)rank * (kCg2BN / 2));
+          mbar_wait(uempty(s), ph ^ 1u);
+          if (elect_one()) {
+            if (urank == 0) mbar_expect_tx(ufull(s), 2u * STAGE);           // the leader's barrier counts both CTAs' bytes
+            const uint32_t sa = uring + (uint32_t)s * STAGE;
+            tma2_load_3d(sa, &tmA, ufull(s), a.chunk_col[q], m0 + a.chunk_off[q], b);
+            tma2_load_2d(sa + A_BYTES, &tmBh, ufull(s), q * BK, n0 + (int)urank * (kCg2BN / 2));
+          }
           if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
-        if (RES) {   // this CTA's residual tile, one column half per epilogue group, on the CTA's OWN barriers
+        if (RES) {   // this CTA's residual tile, one column slice per epilogue group, on the CTA's OWN barriers
           for (int g = 0; g < NG; ++g) {
-            if (it > 0) mbar_wait(rempty_bar(g), (uint32_t)(it - 1) & 1u);
-            mbar_expect_tx(rfull_bar(g), RBUF);
-            for (int bx = 0; bx < CW / 64; ++bx) tma_load_3d(rbuf(g) + (uint32_t)bx * 16384u, &tmR, rfull_bar(g), n0 + g * CW + 64 * bx, m0, b);
+            if (it > 0) mbar_wait(ubars + 416u + 8u * g, (uint32_t)(it - 1) & 1u);
+            if (elect_one()) {
+              const uint32_t rb = ubars + 1024u + (uint32_t)g * (RBUF + 1024u), rf = ubars + 384u + 8u * g;
+              mbar_expect_tx(rf, RBUF);
+              for (int bx = 0; bx < CW / 64; ++bx) tma_load_3d(rb + (uint32_t)bx * 16384u, &tmR, rf, n0 + g * CW + 64 * bx, m0, b);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0 && lane == 0) {
+    // ===================== MMA issuer (leader CTA only; whole warp runs the loop, one elected lane issues) =====================
+    // (with the loop under `lane == 0` every tcgen05.mma sits in an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence of ~130 clocks:
+    //  more than the 128 clocks an M = 256, N = 256, K = 16 MMA needs, twice what N = 128 needs)
+    if (rank == 0) {
+      const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0), ubars = __shfl_sync(0xffffffffu, bars, 0);
+      const uint32_t uring = __shfl_sync(0xffffffffu, ring, 0), utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+      auto ufull = [&](int s) { return ubars + 8u * s; };
+      auto uempty = [&](int s) { return ubars + 8u * (a.stages + s); };
+      auto utfull = [&](int i) { return ubars + 8u * (2 * a.stages + i); };
+      auto utempty = [&](int i) { return ubars + 8u * (2 * a.stages + 2 + i); };
       // D = F32, A = B = BF16, K-major, N = 256, M = 256 (cta_group::2)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCg2BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int s = 0, has = 0;
       uint32_t ph = 0, hph = 0;
       for (int it = 0; it < my_units; ++it) {
         const int acc = it & 1;
-        mbar_wait(tempty_bar(acc), (((uint32_t)(it >> 1)) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
+        mbar_wait(utempty(acc), (((uint32_t)(it >> 1)) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kCg2BN);
+        const uint32_t tmem_d = utmem + (uint32_t)(acc * kCg2BN);
         if (halo) {
           for (int cc = 0; cc < a.halo_cc; ++cc) {
-            mbar_wait(afull_bar(has), hph);
-            const uint32_t xa = base + (uint32_t)has * HALO_SLOT;
+            mbar_wait(ubars + 448u + 8u * has, hph);
+            const uint32_t xa = ubase + (uint32_t)has * HALO_SLOT;
             for (int j = 0; j < a.halo_taps; ++j) {
-              mbar_wait(full_bar(s), ph);
+              mbar_wait(ufull(s), ph);
               tc_fence_after();
-              const uint64_t da = make_desc<BK>(xa + (uint32_t)(j * a.halo_dil) * (uint32_t)(BK * 2)), db = make_desc<BK>(ring + (uint32_t)s * STAGE);
+              const uint64_t da = make_desc<BK>(xa + (uint32_t)(j * a.halo_dil) * (uint32_t)(BK * 2)), db = make_desc<BK>(uring + (uint32_t)s * STAGE);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (cc | j | k) != 0 ? 1u : 0u);
-              umma2_commit_mc(empty_bar(s), (uint16_t)3);
+              for (int k = 0; k < BK / 16; ++k)
+                if (elect_one()) umma2_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (cc | j | k) != 0 ? 1u : 0u);
+              if (elect_one()) umma2_commit_mc(uempty(s), (uint16_t)3);
               if (++s == a.stages) { s = 0; ph ^= 1u; }
             }
-            umma2_commit_mc(aempty_bar(has), (uint16_t)3);   // the halo slots of both CTAs are free once all taps have read them
+            if (elect_one()) umma2_commit_mc(ubars + 480u + 8u * has, (uint16_t)3);   // the halo slots of both CTAs are free once all taps have read them
             if (++has == a.a_stages) { has = 0; hph ^= 1u; }
           }
-          umma2_commit_mc(tfull_bar(acc), (uint16_t)3);
+          if (elect_one()) umma2_commit_mc(utfull(acc), (uint16_t)3);
           continue;
         }
         for (int q = 0; q < a.n_chunks; ++q) {
-          mbar_wait(full_bar(s), ph);
+          mbar_wait(ufull(s), ph);
           tc_fence_after();
-          const uint32_t sa = ring + (uint32_t)s * STAGE;
+          const uint32_t sa = uring + (uint32_t)s * STAGE;
           const uint64_t da = make_desc<BK>(sa), db = make_desc<BK>(sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (q | k) != 0 ? 1u : 0u);
-          umma2_commit_mc(empty_bar(s), (uint16_t)3);   // frees the stage in both CTAs when these MMAs retire
+          for (int k = 0; k < BK / 16; ++k)
+            if (elect_one()) umma2_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (q | k) != 0 ? 1u : 0u);
+          if (elect_one()) umma2_commit_mc(uempty(s), (uint16_t)3);   // frees the stage in both CTAs when these MMAs retire
           if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
-        umma2_commit_mc(tfull_bar(acc), (uint16_t)3);   // accumulators complete in both CTAs
+        if (elect_one()) umma2_commit_mc(utfull(acc), (uint16_t)3);   // accumulators complete in both CTAs
       }
     }
   } else {
