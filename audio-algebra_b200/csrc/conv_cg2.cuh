@@ -84,6 +84,7 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
 }
 
 constexpr int kCg2Threads = 64 + 128;   // TMA warp, MMA warp, one epilogue group
+constexpr int kCg2Threads2 = 64 + 256;  // ... or two (a.n_epi = 2: the groups split the tile's columns)
 constexpr int kCg2ResGroups = 4;           // RES: four epilogue groups, each owns a quarter of the tile's columns
 constexpr int kCg2ResThreads = 64 + 128 * kCg2ResGroups;
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
 // 128 x 128 tile -- so the per-tile epilogue time falls with the number of groups and comes under the short K loop); the
 // residual tile comes in and the result leaves through TMA, in place in the group's SWIZZLE_128B buffer, as in conv_tc_kernel.
 template <int kCg2BN, bool RES>   // N of the pair's tile: 256 (C >= 256 layers) or 128 (the C = 128 k7 layers)
-__global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads2, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmBh,
                                                                   const __grid_constant__ CUtensorMap tmR,
                                                                   const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8 * NG); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), RES ? 8 * NG : 8 * a.n_epi); }
     for (int g = 0; g < NG; ++g) { mbar_init(rfull_bar(g), 1); mbar_init(rempty_bar(g), 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(afull_bar(i), 1); mbar_init(aempty_bar(i), 1); }
     if (halo) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");   // tmR = the halo box map in this mode
@@ -360,59 +361,71 @@ __global__ void __launch_bounds__(RES ? kCg2ResThreads : kCg2Threads, 1) conv_tc
         }
       }
       if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's tile stores are complete
-    } else
-    for (int it = 0; it < my_units; ++it) {
-      const int acc = it & 1;
-      int b, m0, n0;
-      unit_coords(it, b, m0, n0);
-      const bool valid = m0 + row_in_tile < a.lout;
-      const long long tile_off = ((long long)b * a.out_row_stride + m0) * a.cout + n0;
-      if (n0 != bias_n0) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < kCg2BN; i += 128) {
-          const float bv = (n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * i), "f"(bv) : "memory");
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        bias_n0 = n0;
-      }
-      mbar_wait(tfull_bar(acc), ((uint32_t)(it >> 1)) & 1u);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kCg2BN);
-      for (int c0 = 0; c0 < kCg2BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        float bia[32];
+    } else {
+      // non-residual layers: a.n_epi (1 or 2) groups split the tile's columns (an epilogue warp alone on its scheduler is latency
+      // bound; two groups halve the per-tile epilogue time, which matters where the K loop is short relative to the tile: N = 128)
+      const int grp = (warp - 2) >> 2;
+      if (grp < a.n_epi) {
+        const int CWn = kCg2BN / a.n_epi;                    // columns of this group
+        const uint32_t RSn = (uint32_t)CWn * 2u + 16u;
+        const uint32_t gstg = bars + 512u + (uint32_t)grp * ((uint32_t)BM * RSn + (uint32_t)CWn * 4u);
+        const uint32_t gbias = gstg + (uint32_t)BM * RSn;
+        const int vpr = CWn / 8;
+        for (int it = 0; it < my_units; ++it) {
+          const int acc = it & 1;
+          int b, m0, n0;
+          unit_coords(it, b, m0, n0);
+          const int nc = n0 + grp * CWn;
+          const bool valid = m0 + row_in_tile < a.lout;
+          const long long tile_off = ((long long)b * a.out_row_stride + m0) * a.cout + nc;
+          if (n0 != bias_n0) {
+            group_sync(grp);
+            for (int i = et; i < CWn; i += 128) {
+              const float bv = (nc + i < a.cout) ? __ldg(a.bias + nc + i) : 0.f;
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(gbias + 4u * i), "f"(bv) : "memory");
+            }
+            group_sync(grp);
+            bias_n0 = n0;
+          }
+          mbar_wait(tfull_bar(acc), ((uint32_t)(it >> 1)) & 1u);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kCg2BN + grp * CWn);
+          for (int c0 = 0; c0 < CWn; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            float bia[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bia[j]), "=f"(bia[j + 1]), "=f"(bia[j + 2]), "=f"(bia[j + 3])
-                       : "r"(sbias + 4u * (uint32_t)(c0 + j)));
-        const uint32_t srow = stg + (uint32_t)row_in_tile * RS + (uint32_t)c0 * 2u;
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bia[j]), "=f"(bia[j + 1]), "=f"(bia[j + 2]), "=f"(bia[j + 3])
+                           : "r"(gbias + 4u * (uint32_t)(c0 + j)));
+            const uint32_t srow = gstg + (uint32_t)row_in_tile * RSn + (uint32_t)c0 * 2u;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float2 y0 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(bia[8 * g + 0], bia[8 * g + 1]));
-          const float2 y1 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(bia[8 * g + 2], bia[8 * g + 3]));
-          const float2 y2 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bia[8 * g + 4], bia[8 * g + 5]));
-          const float2 y3 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bia[8 * g + 6], bia[8 * g + 7]));
-          uint4 o = make_uint4(pack_bf16(elu2(y0)), pack_bf16(elu2(y1)), pack_bf16(elu2(y2)), pack_bf16(elu2(y3)));
-          if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)g * 16u), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            for (int g = 0; g < 4; ++g) {
+              const float2 y0 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), make_float2(bia[8 * g + 0], bia[8 * g + 1]));
+              const float2 y1 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), make_float2(bia[8 * g + 2], bia[8 * g + 3]));
+              const float2 y2 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), make_float2(bia[8 * g + 4], bia[8 * g + 5]));
+              const float2 y3 = __fadd2_rn(make_float2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), make_float2(bia[8 * g + 6], bia[8 * g + 7]));
+              uint4 o = make_uint4(pack_bf16(elu2(y0)), pack_bf16(elu2(y1)), pack_bf16(elu2(y2)), pack_bf16(elu2(y3)));
+              if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)g * 16u), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc ? tempty1 : tempty0);   // 8 n_epi arrivals: n_epi groups x 4 warps x 2 CTAs
+          group_sync(grp);      // the group's column slice is complete in its staging area
+          for (int idx = et; idx < BM * vpr; idx += 128) {
+            const int rr = idx / vpr, cv = idx % vpr;
+            if (m0 + rr < a.lpad) {
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(gstg + (uint32_t)rr * RSn + (uint32_t)cv * 16u));
+              reinterpret_cast<uint4*>(a.out + tile_off + (long long)rr * a.cout)[cv] = v;
+            }
+          }
+          group_sync(grp);      // staging free for the next tile
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(acc ? tempty1 : tempty0);   // the leader may reuse the accumulator once all 8 warps arrived
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // tile complete in staging
-      for (int idx = et; idx < BM * (kCg2BN / 8); idx += 128) {
-        const int rr = idx / (kCg2BN / 8), cv = idx % (kCg2BN / 8);
-        if (m0 + rr < a.lpad) {
-          uint4 v;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                       : "r"(stg + (uint32_t)rr * RS + (uint32_t)cv * 16u));
-          reinterpret_cast<uint4*>(a.out + tile_off + (long long)rr * a.cout)[cv] = v;
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // staging free for the next tile
     }
   }
 

@@ -871,6 +871,7 @@ struct TcState {
   int nepi_k7_128 = 0, nacc_min = 0;
   int cg2 = 1;                 // wide non-residual layers as cta_group::2 MMAs on CTA pairs (conv_cg2.cuh; AA_TC_CG2=0: one CTA per tile)
   int halo = 1, halo_slots = 2;   // halo mode of the k-tap layers (AA_TC_HALO=0: one activation box per tap, 2: single-CTA kernel only, 3: also N = 128 pairs -- measured slower; AA_TC_HALO_SLOTS: halo boxes in flight)
+  int cg2_nepi = 0;            // epilogue groups of the non-residual pair kernel (0 = default: 2; AA_TC_CG2_NEPI)
   int cg2r = 1;                // ResidualUnit 1x1 layers at C >= 256 on CTA pairs (conv_tc2_kernel<256, true>; AA_TC_CG2R=0: one CTA per tile, 2: + L2 prefetch of the residual)
   int res_tma = 1;             // ResidualUnit 1x1 layers: residual / result tiles through TMA (AA_RES_TMA=0: per-thread loads, staged stores)
 };
@@ -947,6 +948,7 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   if (getenv("AA_TC_NACC")) st->nacc_min = atoi(getenv("AA_TC_NACC"));
   if (getenv("AA_TC_CG2")) st->cg2 = atoi(getenv("AA_TC_CG2"));
   if (getenv("AA_TC_CG2R")) st->cg2r = atoi(getenv("AA_TC_CG2R"));
+  if (getenv("AA_TC_CG2_NEPI")) st->cg2_nepi = atoi(getenv("AA_TC_CG2_NEPI"));
   if (getenv("AA_TC_HALO")) st->halo = atoi(getenv("AA_TC_HALO"));
   if (getenv("AA_TC_HALO_SLOTS")) st->halo_slots = std::max(1, std::min(4, atoi(getenv("AA_TC_HALO_SLOTS"))));
   if (getenv("AA_DEBUG")) fprintf(stderr, "[aa] ru_fused CTAs/SM: C=32 -> %d, C=64 -> %d\n", st->ru_ctas_per_sm[0], st->ru_ctas_per_sm[1]);
@@ -1198,7 +1200,9 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       AA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B half) failed for layer %zu: %d", i, (int)r);
       const int stage2 = BM * 64 * 2 + (kCg2BN / 2) * 64 * 2;
-      const int fixed = pair_res ? 1024 + 1024 + kCg2ResGroups * (BM * (kCg2BN / kCg2ResGroups) * 2 + 1024) : 1024 + 512 + BM * (kCg2BN * 2 + 16) + kCg2BN * 4 + 256;
+      if (!pair_res) a.n_epi = (st->cg2_nepi > 0) ? std::min(2, st->cg2_nepi) : 2;   // column-split epilogue groups (measured: 2 groups -2 ... -4 us per pair layer)
+      const int fixed = pair_res ? 1024 + 1024 + kCg2ResGroups * (BM * (kCg2BN / kCg2ResGroups) * 2 + 1024)
+                                 : 1024 + 512 + BM * (kCg2BN * 2 + 16 * a.n_epi) + kCg2BN * 4 + 256;
       a.stages = std::max(2, std::min(8, (st->max_smem - fixed) / stage2));
       int smem2 = a.stages * stage2 + fixed;
       if (a.halo_rows > 0) {   // halo mode: A slots + a ring of weight halves
@@ -1210,7 +1214,7 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
       const long long units = batch * ((a.m_tiles + 1) / 2) * a.n_tiles_n;
       const int grid2 = (int)std::min<long long>(2 * units, (long long)(aa::num_sms() & ~1));
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3((unsigned)(pair_res ? kCg2ResThreads : kCg2Threads)); cfg.dynamicSmemBytes = (size_t)smem2; cfg.stream = stream;
+      cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3((unsigned)(pair_res ? kCg2ResThreads : 64 + 128 * a.n_epi)); cfg.dynamicSmemBytes = (size_t)smem2; cfg.stream = stream;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
