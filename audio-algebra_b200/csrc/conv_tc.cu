@@ -52,6 +52,7 @@ struct TcArgs {
   // halo mode (stride-1 k-tap layers, non-RES): ONE [halo_rows x 64 channels] activation box per channel chunk serves all taps
   // (tap j = the same box with the descriptor start advanced by j * dil rows), only the weight boxes stream per (chunk, tap)
   int halo_rows, halo_cc, halo_taps, halo_dil, halo_row0, a_stages;   // rows of the box, channel chunks, taps, dilation, row offset of tap 0, A slots
+  int halo_pair;                    // halo mode, one N tile (bn = cout): every weight box serves TWO of the CTA's tiles (two halo boxes, two accumulators)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -222,6 +223,35 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
       int s = 0, has = 0;
       uint32_t ph = 0, hph = 0;
       int it = 0;
+      if (halo && a.halo_pair) {
+        // two tiles of this CTA per pass over the weights (n_tiles_n = 1: every tile uses the same weight boxes)
+        for (long long t = blockIdx.x; t < a.tiles; t += 2LL * gridDim.x) {
+          const long long tB = t + gridDim.x;
+          const int nb = tB < a.tiles ? 2 : 1;
+          for (int cc = 0; cc < a.halo_cc; ++cc) {
+            for (int w = 0; w < nb; ++w) {
+              const long long tt = w ? tB : t;
+              const int b = (int)(tt / tiles_per_b), m0 = (int)(tt % tiles_per_b) * BM;
+              const uint32_t af = ubars + 448u + 8u * has;
+              mbar_wait(ubars + 480u + 8u * has, hph ^ 1u);
+              if (elect_one()) {
+                mbar_expect_tx(af, (uint32_t)a.halo_rows * (uint32_t)(BK * 2));
+                tma_load_3d(ubase + (uint32_t)has * HALO_SLOT, &tmR, af, cc * BK, m0 + a.halo_row0, b);
+              }
+              if (++has == a.a_stages) { has = 0; hph ^= 1u; }
+            }
+            for (int j = 0; j < a.halo_taps; ++j) {
+              const uint32_t fb = ubars + 8u * s;
+              mbar_wait(ubars + 8u * (a.stages + s), ph ^ 1u);
+              if (elect_one()) {
+                mbar_expect_tx(fb, B_BYTES);
+                tma_load_2d(uring + (uint32_t)s * STAGE, &tmB, fb, (j * a.halo_cc + cc) * BK, 0);
+              }
+              if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+          }
+        }
+      } else
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int b = (int)(t / tiles_per_b);
         const int r = (int)(t % tiles_per_b);
@@ -284,6 +314,45 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) conv_tc_kernel(const __grid_
       int s = 0, has = 0;
       uint32_t ph = 0, hph = 0;
       int it = 0;
+      if (halo && a.halo_pair) {
+        for (long long t = blockIdx.x; t < a.tiles; t += 2LL * gridDim.x, it += 2) {
+          const int nb = t + gridDim.x < a.tiles ? 2 : 1;
+          uint32_t tmem_d[2];
+          for (int w = 0; w < nb; ++w) {
+            const int acc = (it + w) % a.n_acc;
+            mbar_wait(ubars + 8u * (2 * a.stages + kMaxAcc + acc), (((uint32_t)((it + w) / a.n_acc)) & 1u) ^ 1u);
+            tmem_d[w] = utmem + (uint32_t)(acc * a.bn);
+          }
+          tc_fence_after();
+          for (int cc = 0; cc < a.halo_cc; ++cc) {
+            uint32_t xa[2];
+            int slot[2];
+            for (int w = 0; w < nb; ++w) {
+              mbar_wait(ubars + 448u + 8u * has, hph);
+              slot[w] = has;
+              xa[w] = ubase + (uint32_t)has * HALO_SLOT;
+              if (++has == a.a_stages) { has = 0; hph ^= 1u; }
+            }
+            for (int j = 0; j < a.halo_taps; ++j) {
+              mbar_wait(ubars + 8u * s, ph);
+              tc_fence_after();
+              const uint64_t db = make_desc<BK>(uring + (uint32_t)s * STAGE);
+              for (int w = 0; w < nb; ++w) {
+                const uint64_t da = make_desc<BK>(xa[w] + (uint32_t)(j * a.halo_dil) * (uint32_t)(BK * 2));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  if (elect_one()) umma_bf16(tmem_d[w], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (cc | j | k) != 0 ? 1u : 0u);
+              }
+              if (elect_one()) umma_commit(ubars + 8u * (a.stages + s));   // frees the weight stage
+              if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+            for (int w = 0; w < nb; ++w)
+              if (elect_one()) umma_commit(ubars + 480u + 8u * slot[w]);   // frees the halo slots
+          }
+          for (int w = 0; w < nb; ++w)
+            if (elect_one()) umma_commit(ubars + 8u * (2 * a.stages + (it + w) % a.n_acc));
+        }
+      } else
       for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
         const int acc = it % a.n_acc;
         mbar_wait(ubars + 8u * (2 * a.stages + kMaxAcc + acc), (((uint32_t)(it / a.n_acc)) & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -871,6 +940,7 @@ struct TcState {
   int nepi_k7_128 = 0, nacc_min = 0;
   int cg2 = 1;                 // wide non-residual layers as cta_group::2 MMAs on CTA pairs (conv_cg2.cuh; AA_TC_CG2=0: one CTA per tile)
   int halo = 1, halo_slots = 2;   // halo mode of the k-tap layers (AA_TC_HALO=0: one activation box per tap, 2: single-CTA kernel only, 3: also N = 128 pairs -- measured slower; AA_TC_HALO_SLOTS: halo boxes in flight)
+  int halo_pair = 0, halo_pair_slots = 4;   // conv_tc_kernel halo mode, dev knob AA_TC_HALO_PAIR=1: two tiles per pass over the weights (correct, measured +-0 / slower)
   int cg2_nepi = 0;            // epilogue groups of the non-residual pair kernel (0 = default: 2; AA_TC_CG2_NEPI)
   int cg2r = 1;                // ResidualUnit 1x1 layers at C >= 256 on CTA pairs (conv_tc2_kernel<256, true>; AA_TC_CG2R=0: one CTA per tile, 2: + L2 prefetch of the residual)
   int res_tma = 1;             // ResidualUnit 1x1 layers: residual / result tiles through TMA (AA_RES_TMA=0: per-thread loads, staged stores)
@@ -949,6 +1019,8 @@ int tc_create(TcState** out, const std::vector<ConvLayer>& layers) {
   if (getenv("AA_TC_CG2")) st->cg2 = atoi(getenv("AA_TC_CG2"));
   if (getenv("AA_TC_CG2R")) st->cg2r = atoi(getenv("AA_TC_CG2R"));
   if (getenv("AA_TC_CG2_NEPI")) st->cg2_nepi = atoi(getenv("AA_TC_CG2_NEPI"));
+  if (getenv("AA_TC_HALO_PAIR")) st->halo_pair = atoi(getenv("AA_TC_HALO_PAIR"));
+  if (getenv("AA_TC_HALO_PAIR_SLOTS")) st->halo_pair_slots = std::max(2, std::min(4, atoi(getenv("AA_TC_HALO_PAIR_SLOTS"))));
   if (getenv("AA_TC_HALO")) st->halo = atoi(getenv("AA_TC_HALO"));
   if (getenv("AA_TC_HALO_SLOTS")) st->halo_slots = std::max(1, std::min(4, atoi(getenv("AA_TC_HALO_SLOTS"))));
   if (getenv("AA_DEBUG")) fprintf(stderr, "[aa] ru_fused CTAs/SM: C=32 -> %d, C=64 -> %d\n", st->ru_ctas_per_sm[0], st->ru_ctas_per_sm[1]);
@@ -1159,6 +1231,11 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
       a.halo_rows = BM + (p.n_taps - 1) * ly.dil; a.halo_cc = ly.cin / 64; a.halo_taps = p.n_taps; a.halo_dil = ly.dil; a.halo_row0 = p.tap_off[0];
       const int slot = (a.halo_rows * 128 + 1023) & ~1023, bstage = (bn * 128 + 1023) & ~1023;
       a.a_stages = st->halo_slots;
+      if (!pair_plain && st->halo_pair && a.n_tiles_n == 1 && 4 * bn <= 512 && a.tiles >= 2LL * aa::num_sms()) {
+        a.halo_pair = 1;                     // two tiles per weight pass: four accumulators, one halo slot per tile and chunk in flight
+        a.n_acc = 4;
+        a.a_stages = std::max(a.a_stages, st->halo_pair_slots);
+      }
       a.stages = std::max(2, std::min(8, (st->max_smem - 2048 - 512 - staging - a.a_stages * slot) / bstage));
       smem = a.a_stages * slot + a.stages * bstage + 1024 + 512 + staging;
       cuuint64_t dims[3] = {(cuuint64_t)p.view_c, (cuuint64_t)view_rows, (cuuint64_t)batch};
