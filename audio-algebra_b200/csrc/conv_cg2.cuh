@@ -1,4 +1,4 @@
-// conv_tc2_kernel -- the wide (bn = 256) non-residual bf16 conv layers as `cta_group::2` MMAs (included by conv_tc.cu).
+// conv_tc2_kernel -- the wide (bn = 256) bf16 conv layers as `cta_group::2` MMAs (included by conv_tc.cu).
 //
 // Why: the k7 layers at C >= 256 are bound by operand streaming INTO the SM (~64 B/clk/SM through TMA): with one
 // CTA per 128 x 256 output tile every K chunk brings 16 KB of activations + 32 KB of weights for 512 clocks of MMAs = 96 B/clk.
@@ -12,8 +12,13 @@
 //   MMA (warp 1 of the leader): wait full[s]; 4 x tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16) -- the hardware reads the A
 //       rows and the B half of each CTA at the same shared-memory offsets; tcgen05.commit.cta_group::2 multicast frees empty[s] in
 //       both CTAs and, after the last chunk, completes tfull[acc] in both;
-//   epilogues (4 warps per CTA): wait own tfull[acc]; TMEM -> +bias -> ELU -> bf16 -> staging -> coalesced stores; arrive on the
-//       LEADER's tempty[acc] (8 arrivals: 4 warps x 2 CTAs) before the leader reuses the accumulator.
+//   epilogues (n_epi groups of 4 warps per CTA, each owning a column slice of the tile): wait own tfull[acc]; TMEM -> +bias -> ELU
+//       -> bf16 -> staging -> coalesced stores; arrive on the LEADER's tempty[acc] (8 n_epi arrivals: groups x 4 warps x 2 CTAs)
+//       before the leader reuses the accumulator.
+// Halo mode (stride-1 k-tap layers): the activations of a channel chunk arrive ONCE per CTA as a [128 + (k - 1) d rows x 64] box in
+// a ring of their own (afull / aempty, both CTAs' boxes on the leader's barrier) and every tap is a row-shifted descriptor view of
+// it; the operand ring then carries the weight halves only.  RES = true: the ResidualUnit 1x1 layers (see the kernel's comment).
+// Producer and MMA warps run their loops with all 32 lanes and elect one per instruction (see elect_one in conv_tc.cu).
 #pragma once
 
 __device__ __forceinline__ uint32_t cluster_rank() {

@@ -2,7 +2,8 @@
 //
 // Activations are kept channels-last in bf16 ([B][L][C], C contiguous) between layers, so that
 //   * an input tile for filter tap j is ONE 3-D TMA box (channels x 128 positions x 1 batch element) whose row
-//     coordinate is simply shifted by the tap offset; conv zero padding = TMA out-of-bounds zero fill;
+//     coordinate is simply shifted by the tap offset; conv zero padding = TMA out-of-bounds zero fill; the stride-1 k7 layers
+//     load one [128 + 6 d rows] halo box per channel chunk instead and address tap j as a row-shifted descriptor view of it;
 //   * strided down-convs (k = 2s, stride s, pad s/2) become a 3-tap stride-1 conv on the view
 //     [B][L/s][s*C] (row offsets -1, 0, +1 with partial column ranges), i.e. the same kernel;
 //   * both MMA operands are K-major: A = activations [128 rows x BK channels], B = weights
