@@ -1174,10 +1174,10 @@ int tc_forward(TcState* st, const std::vector<ConvLayer>& layers, const std::vec
     // (The C = 512 1x1 layers measured 113 us at bn = 128, 110 us at bn = 256 with res_tma, 147 us at bn = 256 without: unchanged
     //  unless the dev knob AA_1X1_BN256=1 is set.)
     if (n_chunks_total == 8 && !last && ly.cout >= 256 && (ly.role != ROLE_RES_SECOND || st->bn_1x1_wide)) bn = 256;
-    // ResidualUnit 1x1 layers at C >= 512: 256-wide tiles on CTA pairs (conv_tc2_kernel<256, true>); measured at B = 64: C = 512
-    // 110 -> 94 us (403 MB of activations = 61 us at the HBM roofline), C = 256 78 -> 79 us (kept on conv_tc_kernel unless AA_TC_CG2R=3)
+    // ResidualUnit 1x1 layers at C >= 256: 256-wide tiles on CTA pairs (conv_tc2_kernel<256, true>); measured at B = 64: C = 512
+    // 110 -> 90 us, C = 256 78 -> 72 us (403 MB of activations = 61 us at the HBM roofline); AA_TC_CG2R=0: conv_tc_kernel
     const bool pair_res = st->cg2 && st->cg2r && ly.role == ROLE_RES_SECOND && !last && p.bk == 64 && p.n_taps == 1 && ly.cout % 256 == 0 &&
-                          (ly.cout >= 512 || st->cg2r >= 3) && ly.elu && rows_padded(lout) >= 2 * BM && aa::num_sms() >= 2;
+                          (ly.cout >= 256 || st->cg2r >= 3) && ly.elu && rows_padded(lout) >= 2 * BM && aa::num_sms() >= 2;
     if (pair_res) bn = 256;
     {
       cuuint64_t dims[2] = {(cuuint64_t)p.k_total, (cuuint64_t)ly.cout};
